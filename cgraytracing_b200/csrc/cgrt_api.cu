@@ -1,0 +1,1009 @@
+// cgrt_api.cu — the C ABI of include/cgrt.h: host-side orchestration of the sm_100a kernels.
+// There is NO CPU fallback anywhere in this file: without a CUDA device cgrt_create fails with CGRT_ERR_NO_DEVICE.
+#include "../../include/cgrt.h"
+
+#include <cmath>
+#include <cstdio>
+#include <cstring>
+#include <string>
+#include <vector>
+
+#include "cgrt_passes.cuh"
+
+#ifdef CGRT_WITH_NCCL
+#include <nccl.h>
+#endif
+
+using namespace cgrt;
+
+namespace {
+
+struct HostTexture {
+    std::vector<uint8_t> rgb;
+    int w, h, isbump;
+    double n[3], p[3], lenx, leny;
+};
+struct HostObject {
+    int kind;
+    double a[3], b[3], r, col[3], refl, transp;
+    int tex, objtype;
+    std::vector<double> tri9;  // mesh
+    std::vector<double> cp;    // bezier
+};
+
+struct BvhBuild {
+    double *tri9 = nullptr;  // original order, device
+    int ntris = 0;
+};
+
+}  // namespace
+
+struct cgrt_ctx {
+    int device = 0;
+    cudaStream_t stream = nullptr;
+    std::string err = "";
+    cgrt_config cfg;
+    PassParams P;
+    std::vector<HostTexture> textures;
+    std::vector<HostObject> objects;
+    bool committed = false;
+    SceneDev S;
+    BvhBuild bvh_src[CGRT_MAX_BVH];
+    int obj_bvh[CGRT_MAX_OBJECTS];
+    std::vector<void *> allocs;
+
+    // hitpoints
+    double *hp_rec = nullptr;  // raw records (12 doubles each), creation order of the wavefront
+    unsigned int hp_cap = 0, hp_count = 0;
+    unsigned int *d_hp_count = nullptr;
+    bool grid_built = false;
+    unsigned int nhp = 0;
+    HpArrays A;
+    void *acc = nullptr;
+    uint32_t *cell_start = nullptr, *pix_start = nullptr, *pix_perm = nullptr;
+
+    // queues
+    RayQueue q[2];
+    DepositQueue dq;
+    unsigned int q_cap = 0, dq_cap = 0;
+    unsigned int *d_qcount = nullptr;  // [0],[1]: ray queues, [2]: deposit queue
+    Counters *d_ctr = nullptr;
+    TravCounters *d_tc = nullptr;
+    uint64_t launches = 0;
+    uint64_t diffuse_hits = 0;
+    double ms[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+    cudaEvent_t ev[2] = {nullptr, nullptr};
+    size_t photon_chunk = 4u << 20;
+};
+
+namespace {
+
+#define CK(call)                                                                                         \
+    do {                                                                                                 \
+        cudaError_t e__ = (call);                                                                        \
+        if (e__ != cudaSuccess) {                                                                        \
+            char b__[512];                                                                               \
+            snprintf(b__, sizeof b__, "%s:%d: %s -> %s", __FILE__, __LINE__, #call, cudaGetErrorString(e__)); \
+            ctx->err = b__;                                                                              \
+            return CGRT_ERR_CUDA;                                                                        \
+        }                                                                                                \
+    } while (0)
+#define CKS(expr)                \
+    do {                         \
+        int s__ = (expr);        \
+        if (s__ != 0) return s__; \
+    } while (0)
+#define FAIL(code, msg)   \
+    do {                  \
+        ctx->err = (msg); \
+        return (code);    \
+    } while (0)
+
+template <typename T>
+int dalloc(cgrt_ctx *ctx, T **p, size_t n) {
+    *p = nullptr;
+    if (n == 0) n = 1;
+    CK(cudaMalloc((void **)p, n * sizeof(T)));
+    ctx->allocs.push_back((void *)*p);
+    return 0;
+}
+int dfree(cgrt_ctx *ctx, void *p) {
+    if (!p) return 0;
+    for (size_t i = 0; i < ctx->allocs.size(); i++)
+        if (ctx->allocs[i] == p) {
+            ctx->allocs[i] = ctx->allocs.back();
+            ctx->allocs.pop_back();
+            break;
+        }
+    CK(cudaFree(p));
+    return 0;
+}
+inline unsigned int nblk(size_t n, unsigned int b) { return (unsigned int)((n + b - 1) / b); }
+
+struct PhaseTimer {
+    cgrt_ctx *ctx;
+    int slot;
+    PhaseTimer(cgrt_ctx *c, int s) : ctx(c), slot(s) { cudaEventRecord(ctx->ev[0], ctx->stream); }
+    void stop() {
+        cudaEventRecord(ctx->ev[1], ctx->stream);
+        cudaEventSynchronize(ctx->ev[1]);
+        float t = 0;
+        cudaEventElapsedTime(&t, ctx->ev[0], ctx->ev[1]);
+        ctx->ms[slot] += t;
+    }
+};
+
+// ---- radix sort driver: keys (dev) -> sorted keys + permutation (dev). nbits rounded up to whole 8-bit digits.
+int radix_sort_dev(cgrt_ctx *ctx, size_t n, const uint64_t *keys_in, int nbits, uint64_t *keys_out, uint32_t *perm_out) {
+    if (n == 0) return 0;
+    if (n >= (1ull << 32)) FAIL(CGRT_ERR_CAPACITY, "radix sort: more than 2^32 keys");
+    int passes = (nbits + 7) / 8;
+    if (passes < 1) passes = 1;
+    int ntiles = (int)((n + RS_TILE - 1) / RS_TILE);
+    uint64_t *kb[2];
+    uint32_t *vb[2];
+    uint32_t *counts;
+    CKS(dalloc(ctx, &kb[0], n));
+    CKS(dalloc(ctx, &kb[1], n));
+    CKS(dalloc(ctx, &vb[0], n));
+    CKS(dalloc(ctx, &vb[1], n));
+    CKS(dalloc(ctx, &counts, (size_t)256 * ntiles));
+    const uint64_t *src_k = keys_in;
+    const uint32_t *src_v = nullptr;
+    int cur = 0;
+    for (int p = 0; p < passes; p++) {
+        int shift = 8 * p;
+        rs_hist_kernel<<<ntiles, RS_THREADS, 0, ctx->stream>>>(src_k, (int64_t)n, shift, counts, ntiles);
+        rs_scan_kernel<<<1, 1024, 0, ctx->stream>>>(counts, (int64_t)256 * ntiles);
+        rs_scatter_kernel<<<ntiles, RS_THREADS, 0, ctx->stream>>>(src_k, src_v, kb[cur], vb[cur], (int64_t)n, shift, counts, ntiles, p == 0);
+        ctx->launches += 3;
+        src_k = kb[cur];
+        src_v = vb[cur];
+        cur ^= 1;
+    }
+    CK(cudaMemcpyAsync(keys_out, src_k, n * sizeof(uint64_t), cudaMemcpyDeviceToDevice, ctx->stream));
+    CK(cudaMemcpyAsync(perm_out, src_v, n * sizeof(uint32_t), cudaMemcpyDeviceToDevice, ctx->stream));
+    CK(cudaStreamSynchronize(ctx->stream));
+    CK(cudaGetLastError());
+    CKS(dfree(ctx, kb[0])); CKS(dfree(ctx, kb[1])); CKS(dfree(ctx, vb[0])); CKS(dfree(ctx, vb[1])); CKS(dfree(ctx, counts));
+    return 0;
+}
+
+// ---- LBVH build over n triangles already on the device (tri9, original order)
+int build_bvh(cgrt_ctx *ctx, double *tri9_dev, int n, double orient_sign, int slot) {
+    BvhDev &B = ctx->S.bvh[slot];
+    memset(&B, 0, sizeof B);
+    B.ntris = n;
+    B.orient_sign = orient_sign;
+    B.root_is_leaf = (n == 1);
+    ctx->bvh_src[slot].tri9 = tri9_dev;
+    ctx->bvh_src[slot].ntris = n;
+    if (n <= 0) FAIL(CGRT_ERR_INVALID, "mesh with no triangles");
+    const unsigned int T = 256;
+    uint32_t *bounds;
+    uint64_t *keys, *keys_sorted;
+    uint32_t *perm;
+    CKS(dalloc(ctx, &bounds, 6));
+    CKS(dalloc(ctx, &keys, (size_t)n));
+    CKS(dalloc(ctx, &keys_sorted, (size_t)n));
+    CKS(dalloc(ctx, &perm, (size_t)n));
+    uint32_t init[6] = {0xffffffffu, 0xffffffffu, 0xffffffffu, 0u, 0u, 0u};
+    CK(cudaMemcpyAsync(bounds, init, sizeof init, cudaMemcpyHostToDevice, ctx->stream));
+    lbvh_bounds_kernel<<<nblk(n, T), T, 0, ctx->stream>>>(tri9_dev, n, bounds);
+    lbvh_morton_kernel<<<nblk(n, T), T, 0, ctx->stream>>>(tri9_dev, n, bounds, keys);
+    ctx->launches += 2;
+    CKS(radix_sort_dev(ctx, (size_t)n, keys, 30, keys_sorted, perm));
+
+    TriRec *tris;
+    int *tri_id;
+    float *box;
+    BvhNode *nodes;
+    int *left, *right, *parent;
+    unsigned int *flags;
+    int ninternal = n > 1 ? n - 1 : 0;
+    CKS(dalloc(ctx, &tris, (size_t)n));
+    CKS(dalloc(ctx, &tri_id, (size_t)n));
+    CKS(dalloc(ctx, &box, (size_t)(2 * n) * 6));
+    CKS(dalloc(ctx, &nodes, (size_t)(ninternal > 0 ? ninternal : 1)));
+    CKS(dalloc(ctx, &left, (size_t)n));
+    CKS(dalloc(ctx, &right, (size_t)n));
+    CKS(dalloc(ctx, &parent, (size_t)(2 * n)));
+    CKS(dalloc(ctx, &flags, (size_t)n));
+    CK(cudaMemsetAsync(flags, 0, sizeof(unsigned int) * n, ctx->stream));
+    CK(cudaMemsetAsync(parent, 0xff, sizeof(int) * 2 * n, ctx->stream));
+    lbvh_leaves_kernel<<<nblk(n, T), T, 0, ctx->stream>>>(tri9_dev, perm, n, tris, tri_id, box);
+    ctx->launches++;
+    if (ninternal > 0) {
+        lbvh_hierarchy_kernel<<<nblk(ninternal, T), T, 0, ctx->stream>>>(keys_sorted, n, left, right, parent);
+        lbvh_refit_kernel<<<nblk(n, T), T, 0, ctx->stream>>>(n, left, right, parent, box, flags);
+        lbvh_pack_kernel<<<nblk(ninternal, T), T, 0, ctx->stream>>>(n, left, right, box, nodes);
+        ctx->launches += 3;
+    }
+    CK(cudaStreamSynchronize(ctx->stream));
+    CK(cudaGetLastError());
+    B.nodes = nodes;
+    B.tris = tris;
+    B.tri_id = tri_id;
+    CKS(dfree(ctx, bounds)); CKS(dfree(ctx, keys)); CKS(dfree(ctx, keys_sorted)); CKS(dfree(ctx, perm));
+    CKS(dfree(ctx, box)); CKS(dfree(ctx, left)); CKS(dfree(ctx, right)); CKS(dfree(ctx, parent)); CKS(dfree(ctx, flags));
+    return 0;
+}
+
+// Per-mesh orientation sign: sum of pa . (pb x pc) in triangle order; >= 0 -> winding normals point outward.
+double orientation_sign(const double *tri9, size_t n) {
+    double vol = 0.0;
+    for (size_t i = 0; i < n; i++) {
+        const double *t = tri9 + 9 * i;
+        d3 pa = mk(t[0], t[1], t[2]), pb = mk(t[3], t[4], t[5]), pc = mk(t[6], t[7], t[8]);
+        vol += dot(pa, cross(pb, pc));
+    }
+    return (vol >= 0.0) ? 1.0 : -1.0;
+}
+
+int alloc_queue(cgrt_ctx *ctx, RayQueue &q, size_t cap, bool with_aux) {
+    double *base;
+    CKS(dalloc(ctx, &base, cap * 9));
+    q.ox = base; q.oy = base + cap; q.oz = base + 2 * cap;
+    q.dx = base + 3 * cap; q.dy = base + 4 * cap; q.dz = base + 5 * cap;
+    q.wx = base + 6 * cap; q.wy = base + 7 * cap; q.wz = base + 8 * cap;
+    CKS(dalloc(ctx, &q.id, cap));
+    q.aux = nullptr;
+    if (with_aux) CKS(dalloc(ctx, &q.aux, cap));
+    return 0;
+}
+int free_queue(cgrt_ctx *ctx, RayQueue &q) {
+    CKS(dfree(ctx, q.ox)); CKS(dfree(ctx, q.id)); CKS(dfree(ctx, q.aux));
+    memset(&q, 0, sizeof q);
+    return 0;
+}
+int ensure_queues(cgrt_ctx *ctx, size_t cap) {
+    if (cap <= ctx->q_cap) return 0;
+    if (ctx->q_cap) {
+        CKS(free_queue(ctx, ctx->q[0])); CKS(free_queue(ctx, ctx->q[1]));
+        CKS(dfree(ctx, ctx->dq.px));
+    }
+    CKS(alloc_queue(ctx, ctx->q[0], cap, true));
+    CKS(alloc_queue(ctx, ctx->q[1], cap, true));
+    double *base;
+    CKS(dalloc(ctx, &base, cap * 9));
+    DepositQueue &d = ctx->dq;
+    d.px = base; d.py = base + cap; d.pz = base + 2 * cap; d.nx = base + 3 * cap; d.ny = base + 4 * cap; d.nz = base + 5 * cap;
+    d.fx = base + 6 * cap; d.fy = base + 7 * cap; d.fz = base + 8 * cap;
+    ctx->q_cap = (unsigned int)cap;
+    ctx->dq_cap = (unsigned int)cap;
+    return 0;
+}
+
+int ensure_hp_capacity(cgrt_ctx *ctx, size_t need) {
+    if (need <= ctx->hp_cap) return 0;
+    size_t cap = ctx->hp_cap ? ctx->hp_cap : 1024;
+    while (cap < need) cap = cap + cap / 2 + 1024;
+    if (cap >= (1ull << 32)) FAIL(CGRT_ERR_CAPACITY, "more than 2^32 hitpoints");
+    double *nrec;
+    CKS(dalloc(ctx, &nrec, cap * 12));
+    if (ctx->hp_rec) {
+        CK(cudaMemcpyAsync(nrec, ctx->hp_rec, (size_t)ctx->hp_count * 12 * sizeof(double), cudaMemcpyDeviceToDevice, ctx->stream));
+        CK(cudaStreamSynchronize(ctx->stream));
+        CKS(dfree(ctx, ctx->hp_rec));
+    }
+    ctx->hp_rec = nrec;
+    ctx->hp_cap = (unsigned int)cap;
+    return 0;
+}
+
+void derive_params(cgrt_ctx *ctx) {
+    const cgrt_config &c = ctx->cfg;
+    PassParams &P = ctx->P;
+    P.width = c.width; P.height = c.height; P.max_depth = c.max_depth; P.samples = c.num_of_samples; P.use_dof = c.use_dof;
+    P.hashsize = (uint32_t)c.hashsize;
+    // Hashtable(hashsize, r): hash.h:22-30 with r = 200.0/height (main.cpp:183)
+    double r = 200.0 / c.height;
+    int cells = (int)(std::ceil(70.0 / r));
+    P.celllength = 70.0 / cells;
+    P.r2_init = r * r;
+    P.alpha = c.alpha; P.focus_plane = c.focus_plane; P.lens_radius = c.lens_radius;
+    for (int i = 0; i < 3; i++) { P.cam[i] = c.camorg[i]; P.light[i] = c.lightorg[i]; }
+    P.seed = c.seed;
+}
+
+}  // namespace
+
+namespace {
+template <typename T>
+int upload(cgrt_ctx *ctx, T **d, const T *h, size_t n) {
+    CKS(dalloc(ctx, d, n));
+    CK(cudaMemcpyAsync(*d, h, n * sizeof(T), cudaMemcpyHostToDevice, ctx->stream));
+    return 0;
+}
+template <typename T>
+int download_free(cgrt_ctx *ctx, T *h, T *d, size_t n) {
+    if (h) CK(cudaMemcpyAsync(h, d, n * sizeof(T), cudaMemcpyDeviceToHost, ctx->stream));
+    CK(cudaStreamSynchronize(ctx->stream));
+    return dfree(ctx, d);
+}
+}  // namespace
+
+// =================================================================================================================
+extern "C" {
+
+int cgrt_version(void) { return 100; }
+
+void cgrt_default_config(cgrt_config *c) {
+    memset(c, 0, sizeof *c);
+    c->width = 1024; c->height = 768; c->max_depth = 5; c->num_of_samples = 1; c->use_dof = 0; c->hashsize = 1000001;
+    c->accum_mode = 0;
+    c->alpha = 0.7; c->focus_plane = 20.0; c->lens_radius = 1.5;
+    c->lightorg[0] = 0; c->lightorg[1] = 19.999; c->lightorg[2] = 20;
+    c->camorg[0] = 0; c->camorg[1] = 0; c->camorg[2] = -10;
+    c->seed = 20261018ull;
+}
+
+int cgrt_create(int device, cgrt_ctx **out) {
+    if (!out) return CGRT_ERR_INVALID;
+    *out = nullptr;
+    int ndev = 0;
+    if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev <= 0 || device < 0 || device >= ndev) return CGRT_ERR_NO_DEVICE;
+    if (cudaSetDevice(device) != cudaSuccess) return CGRT_ERR_NO_DEVICE;
+    cgrt_ctx *ctx = new cgrt_ctx();
+    ctx->device = device;
+    cgrt_default_config(&ctx->cfg);
+    derive_params(ctx);
+    memset(&ctx->S, 0, sizeof ctx->S);
+    memset(&ctx->A, 0, sizeof ctx->A);
+    memset(ctx->q, 0, sizeof ctx->q);
+    memset(&ctx->dq, 0, sizeof ctx->dq);
+    if (cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking) != cudaSuccess || cudaEventCreate(&ctx->ev[0]) != cudaSuccess ||
+        cudaEventCreate(&ctx->ev[1]) != cudaSuccess) {
+        delete ctx;
+        return CGRT_ERR_CUDA;
+    }
+    if (dalloc(ctx, &ctx->d_hp_count, 1) || dalloc(ctx, &ctx->d_qcount, 4) || dalloc(ctx, &ctx->d_ctr, 1) || dalloc(ctx, &ctx->d_tc, 1)) {
+        delete ctx;
+        return CGRT_ERR_CUDA;
+    }
+    cudaMemset(ctx->d_hp_count, 0, sizeof(unsigned int));
+    cudaMemset(ctx->d_qcount, 0, 4 * sizeof(unsigned int));
+    cudaMemset(ctx->d_ctr, 0, sizeof(Counters));
+    cudaMemset(ctx->d_tc, 0, sizeof(TravCounters));
+    *out = ctx;
+    return CGRT_OK;
+}
+
+int cgrt_destroy(cgrt_ctx *ctx) {
+    if (!ctx) return CGRT_OK;
+    cudaSetDevice(ctx->device);
+    cudaStreamSynchronize(ctx->stream);
+    for (void *p : ctx->allocs) cudaFree(p);
+    if (ctx->ev[0]) cudaEventDestroy(ctx->ev[0]);
+    if (ctx->ev[1]) cudaEventDestroy(ctx->ev[1]);
+    if (ctx->stream) cudaStreamDestroy(ctx->stream);
+    delete ctx;
+    return CGRT_OK;
+}
+
+const char *cgrt_last_error(const cgrt_ctx *ctx) { return ctx ? ctx->err.c_str() : "null context"; }
+
+int cgrt_set_config(cgrt_ctx *ctx, const cgrt_config *cfg) {
+    if (!ctx || !cfg) return CGRT_ERR_INVALID;
+    if (cfg->width <= 0 || cfg->height <= 0 || cfg->hashsize <= 0 || cfg->num_of_samples <= 0 || cfg->max_depth <= 0)
+        FAIL(CGRT_ERR_INVALID, "config: non-positive size");
+    if ((uint64_t)cfg->width * cfg->height * cfg->num_of_samples >= (1ull << 28))
+        FAIL(CGRT_ERR_CAPACITY, "config: width*height*samples must be < 2^28 (creation sequence is 32 bits)");
+    if (cfg->max_depth > 5) FAIL(CGRT_ERR_CAPACITY, "config: max_depth > 5 needs more than 4 DFS bits");
+    if (ctx->hp_count) FAIL(CGRT_ERR_INVALID, "config cannot change after the eye pass");
+    ctx->cfg = *cfg;
+    derive_params(ctx);
+    return CGRT_OK;
+}
+int cgrt_get_stream(cgrt_ctx *ctx, void **stream) {
+    if (!ctx || !stream) return CGRT_ERR_INVALID;
+    *stream = (void *)ctx->stream;
+    return CGRT_OK;
+}
+int cgrt_synchronize(cgrt_ctx *ctx) {
+    if (!ctx) return CGRT_ERR_INVALID;
+    CK(cudaStreamSynchronize(ctx->stream));
+    return CGRT_OK;
+}
+
+// ---- scene ---------------------------------------------------------------------------------------------------------
+int cgrt_add_texture(cgrt_ctx *ctx, const uint8_t *rgb, int w, int h, const double n[3], const double p[3], double lenx, double leny,
+                     int isbump, int *tex_id) {
+    if (!ctx || !rgb || w <= 0 || h <= 0) return CGRT_ERR_INVALID;
+    if (ctx->committed) FAIL(CGRT_ERR_INVALID, "scene already committed");
+    if (ctx->textures.size() >= CGRT_MAX_TEX) FAIL(CGRT_ERR_CAPACITY, "too many textures");
+    HostTexture t;
+    t.rgb.assign(rgb, rgb + (size_t)w * h * 3);
+    t.w = w; t.h = h; t.isbump = isbump != 0; t.lenx = lenx; t.leny = leny;
+    for (int i = 0; i < 3; i++) { t.n[i] = n[i]; t.p[i] = p[i]; }
+    ctx->textures.push_back(std::move(t));
+    if (tex_id) *tex_id = (int)ctx->textures.size() - 1;
+    return CGRT_OK;
+}
+static int add_object(cgrt_ctx *ctx, HostObject &&o, int *obj_id) {
+    if (ctx->committed) FAIL(CGRT_ERR_INVALID, "scene already committed");
+    if (ctx->objects.size() >= CGRT_MAX_OBJECTS) FAIL(CGRT_ERR_CAPACITY, "too many objects");
+    ctx->objects.push_back(std::move(o));
+    if (obj_id) *obj_id = (int)ctx->objects.size() - 1;
+    return CGRT_OK;
+}
+int cgrt_add_sphere(cgrt_ctx *ctx, const double c[3], double r, const double col[3], double refl, double transp, int *obj_id) {
+    if (!ctx || !c || !col) return CGRT_ERR_INVALID;
+    HostObject o{};
+    o.kind = OBJ_SPHERE; o.r = r; o.refl = refl; o.transp = transp; o.tex = -1; o.objtype = 0;
+    for (int i = 0; i < 3; i++) { o.a[i] = c[i]; o.col[i] = col[i]; }
+    return add_object(ctx, std::move(o), obj_id);
+}
+int cgrt_add_plane(cgrt_ctx *ctx, const double p[3], const double n[3], const double col[3], double refl, double transp, int tex_id, int *obj_id) {
+    if (!ctx || !p || !n || !col) return CGRT_ERR_INVALID;
+    if (tex_id >= (int)ctx->textures.size()) FAIL(CGRT_ERR_INVALID, "unknown texture id");
+    HostObject o{};
+    o.kind = OBJ_PLANE; o.refl = refl; o.transp = transp; o.tex = tex_id < 0 ? -1 : tex_id; o.objtype = 0;
+    for (int i = 0; i < 3; i++) { o.a[i] = p[i]; o.b[i] = n[i]; o.col[i] = col[i]; }
+    return add_object(ctx, std::move(o), obj_id);
+}
+int cgrt_add_mesh(cgrt_ctx *ctx, const double *tri9, int ntri, const double col[3], double refl, double transp, int objtype, int *obj_id) {
+    if (!ctx || !tri9 || ntri <= 0 || !col) return CGRT_ERR_INVALID;
+    HostObject o{};
+    o.kind = OBJ_MESH; o.refl = refl; o.transp = transp; o.tex = -1; o.objtype = objtype;
+    for (int i = 0; i < 3; i++) o.col[i] = col[i];
+    o.tri9.assign(tri9, tri9 + (size_t)ntri * 9);
+    return add_object(ctx, std::move(o), obj_id);
+}
+int cgrt_add_bezier(cgrt_ctx *ctx, const double *cp3, int ncp, const double pos[3], const double col[3], double refl, double transp, int *obj_id) {
+    if (!ctx || !cp3 || ncp < 2 || ncp > CGRT_MAX_CP || !pos || !col) return CGRT_ERR_INVALID;
+    HostObject o{};
+    o.kind = OBJ_BEZIER; o.refl = refl; o.transp = transp; o.tex = -1; o.objtype = 0;
+    for (int i = 0; i < 3; i++) { o.a[i] = pos[i]; o.col[i] = col[i]; }
+    o.cp.assign(cp3, cp3 + (size_t)ncp * 3);
+    return add_object(ctx, std::move(o), obj_id);
+}
+
+int cgrt_commit_scene(cgrt_ctx *ctx) {
+    if (!ctx) return CGRT_ERR_INVALID;
+    if (ctx->committed) FAIL(CGRT_ERR_INVALID, "scene already committed");
+    CK(cudaSetDevice(ctx->device));
+    SceneDev &S = ctx->S;
+    memset(&S, 0, sizeof S);
+    std::vector<double *> heights(ctx->textures.size(), nullptr);
+    // textures (K5) + height tables (texture.h:27-37; exp() on the host so the table is bit-identical to the reference's)
+    for (size_t t = 0; t < ctx->textures.size(); t++) {
+        const HostTexture &ht = ctx->textures[t];
+        size_t nt = (size_t)ht.w * ht.h;
+        uint8_t *raw;
+        uchar4 *tex;
+        CKS(dalloc(ctx, &raw, nt * 3));
+        CKS(dalloc(ctx, &tex, nt));
+        CK(cudaMemcpyAsync(raw, ht.rgb.data(), nt * 3, cudaMemcpyHostToDevice, ctx->stream));
+        texture_stage_kernel<<<nblk(nt, 256), 256, 0, ctx->stream>>>(raw, (int64_t)nt, tex);
+        ctx->launches++;
+        CK(cudaStreamSynchronize(ctx->stream));
+        CKS(dfree(ctx, raw));
+        TexDev &T = S.tex[t];
+        T.texels = tex; T.W = ht.w; T.H = ht.h; T.isbump = ht.isbump; T.lenx = ht.lenx; T.leny = ht.leny;
+        for (int i = 0; i < 3; i++) { T.n[i] = ht.n[i]; T.p[i] = ht.p[i]; }
+        if (ht.isbump) {
+            std::vector<double> hh(nt);
+            const double coeff = 0.5;
+            for (size_t i = 0; i < nt; i++) {
+                double r = (double)ht.rgb[3 * i] / (double)256, g = (double)ht.rgb[3 * i + 1] / (double)256, b = (double)ht.rgb[3 * i + 2] / (double)256;
+                double v = (0.299 * r + 0.587 * g + 0.114 * b);
+                v = 1 - std::exp(-3.3 * v);
+                v *= coeff;
+                hh[i] = v;
+            }
+            CKS(dalloc(ctx, &heights[t], nt));
+            CK(cudaMemcpyAsync(heights[t], hh.data(), nt * sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
+            CK(cudaStreamSynchronize(ctx->stream));
+        }
+    }
+    S.ntex = (int)ctx->textures.size();
+    int nbvh = 0, nbez = 0;
+    S.nobj = (int)ctx->objects.size();
+    for (int i = 0; i < S.nobj; i++) {
+        const HostObject &ho = ctx->objects[i];
+        ObjDev &O = S.obj[i];
+        O.kind = ho.kind; O.tex = ho.tex; O.bvh = -1; O.objtype = ho.objtype; O.aux = 0;
+        O.r = ho.r; O.r2 = ho.r * ho.r; O.refl = ho.refl; O.transp = ho.transp;
+        for (int k = 0; k < 3; k++) { O.a[k] = ho.a[k]; O.b[k] = ho.b[k]; O.col[k] = ho.col[k]; }
+        // main.cpp:82,129,135
+        O.material = (ho.refl < CGRT_EPS && ho.transp < CGRT_EPS) ? MAT_DIFFUSE : (ho.transp < CGRT_EPS ? MAT_MIRROR : MAT_GLASS);
+        ctx->obj_bvh[i] = -1;
+        if (ho.kind == OBJ_MESH) {
+            if (nbvh >= CGRT_MAX_BVH) FAIL(CGRT_ERR_CAPACITY, "too many meshes");
+            int n = (int)(ho.tri9.size() / 9);
+            double *tri9;
+            CKS(dalloc(ctx, &tri9, ho.tri9.size()));
+            CK(cudaMemcpyAsync(tri9, ho.tri9.data(), ho.tri9.size() * sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
+            CKS(build_bvh(ctx, tri9, n, orientation_sign(ho.tri9.data(), (size_t)n), nbvh));
+            O.bvh = nbvh; ctx->obj_bvh[i] = nbvh; nbvh++;
+        } else if (ho.kind == OBJ_PLANE && ho.tex >= 0) {
+            const HostTexture &ht = ctx->textures[ho.tex];
+            // objects.h:482: only an n.y == 1 plane with a bump texture gets the displaced mesh
+            if (std::fabs(ho.b[1] - 1.0) < 1e-5 && ht.isbump && ht.h / 3 - 1 > 0 && ht.w / 3 - 1 > 0) {
+                if (nbvh >= CGRT_MAX_BVH) FAIL(CGRT_ERR_CAPACITY, "too many meshes");
+                int ncell = (ht.h / 3 - 1) * (ht.w / 3 - 1);
+                int n = 2 * ncell;
+                double *tri9;
+                CKS(dalloc(ctx, &tri9, (size_t)n * 9));
+                bump_triangles_kernel<<<nblk(ncell, 256), 256, 0, ctx->stream>>>(heights[ho.tex], ht.h, ht.w, ht.p[0], ht.p[2], ht.lenx, ht.leny, ho.a[1], tri9);
+                ctx->launches++;
+                std::vector<double> host((size_t)n * 9);
+                CK(cudaMemcpyAsync(host.data(), tri9, host.size() * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
+                CK(cudaStreamSynchronize(ctx->stream));
+                CKS(build_bvh(ctx, tri9, n, orientation_sign(host.data(), (size_t)n), nbvh));
+                O.bvh = nbvh; ctx->obj_bvh[i] = nbvh; nbvh++;
+            }
+        } else if (ho.kind == OBJ_BEZIER) {
+            if (nbez >= CGRT_MAX_BEZIER) FAIL(CGRT_ERR_CAPACITY, "too many Bezier objects");
+            BezDev &Z = S.bez[nbez];
+            Z.ncp = (int)(ho.cp.size() / 3);
+            double max_z = -1e10, max_y = -1e10, min_y = 1e10;  // bezier.h:50-63
+            for (int k = 0; k < Z.ncp; k++) {
+                for (int c = 0; c < 3; c++) Z.cp[k][c] = ho.cp[3 * k + c];
+                if (Z.cp[k][2] > max_z) max_z = Z.cp[k][2];
+                if (Z.cp[k][1] > max_y) max_y = Z.cp[k][1];
+                if (Z.cp[k][1] < min_y) min_y = Z.cp[k][1];
+            }
+            for (int c = 0; c < 3; c++) Z.pos[c] = ho.a[c];
+            Z.box[0] = max_z + ho.a[0]; Z.box[1] = -max_z + ho.a[0];
+            Z.box[2] = max_y + ho.a[1]; Z.box[3] = min_y + ho.a[1];
+            Z.box[4] = max_z + ho.a[2]; Z.box[5] = -max_z + ho.a[2];
+            double rz = Z.cp[Z.ncp - 1][2];
+            Z.umin_r2 = rz * rz;
+            O.aux = nbez++;
+        }
+    }
+    S.nbvh = nbvh;
+    S.nbez = nbez;
+    for (double *h : heights) CKS(dfree(ctx, h));
+    ctx->committed = true;
+    return CGRT_OK;
+}
+
+// ---- parity hooks ------------------------------------------------------------------------------------------------
+
+static int intersect_impl(cgrt_ctx *ctx, int64_t n, const double *org, const double *dir, double *t, double *nrm, double *nrm_raw, int32_t *obj,
+                          int32_t *into, int32_t *prim, bool count, uint64_t *nv, uint64_t *tt) {
+    if (!ctx || n < 0 || !org || !dir) return CGRT_ERR_INVALID;
+    if (!ctx->committed) FAIL(CGRT_ERR_INVALID, "commit the scene first");
+    if (n == 0) return CGRT_OK;
+    CK(cudaSetDevice(ctx->device));
+    double *d_org, *d_dir, *d_t, *d_n, *d_nr;
+    int *d_obj, *d_into, *d_prim;
+    CKS(upload(ctx, &d_org, org, (size_t)n * 3));
+    CKS(upload(ctx, &d_dir, dir, (size_t)n * 3));
+    CKS(dalloc(ctx, &d_t, (size_t)n)); CKS(dalloc(ctx, &d_n, (size_t)n * 3)); CKS(dalloc(ctx, &d_nr, (size_t)n * 3));
+    CKS(dalloc(ctx, &d_obj, (size_t)n)); CKS(dalloc(ctx, &d_into, (size_t)n)); CKS(dalloc(ctx, &d_prim, (size_t)n));
+    CK(cudaMemsetAsync(ctx->d_tc, 0, sizeof(TravCounters), ctx->stream));
+    if (count) intersect_batch_kernel<true><<<nblk(n, 128), 128, 0, ctx->stream>>>(ctx->S, n, d_org, d_dir, d_t, d_n, d_nr, d_obj, d_into, d_prim, ctx->d_tc);
+    else intersect_batch_kernel<false><<<nblk(n, 128), 128, 0, ctx->stream>>>(ctx->S, n, d_org, d_dir, d_t, d_n, d_nr, d_obj, d_into, d_prim, ctx->d_tc);
+    ctx->launches++;
+    CK(cudaGetLastError());
+    CKS(download_free(ctx, t, d_t, (size_t)n));
+    CKS(download_free(ctx, nrm, d_n, (size_t)n * 3));
+    CKS(download_free(ctx, nrm_raw, d_nr, (size_t)n * 3));
+    CKS(download_free(ctx, (int *)obj, d_obj, (size_t)n));
+    CKS(download_free(ctx, (int *)into, d_into, (size_t)n));
+    CKS(download_free(ctx, (int *)prim, d_prim, (size_t)n));
+    CKS(dfree(ctx, d_org)); CKS(dfree(ctx, d_dir));
+    if (count) {
+        TravCounters tc;
+        CK(cudaMemcpy(&tc, ctx->d_tc, sizeof tc, cudaMemcpyDeviceToHost));
+        if (nv) *nv = tc.node_visits;
+        if (tt) *tt = tc.tri_tests;
+    }
+    return CGRT_OK;
+}
+int cgrt_intersect_batch(cgrt_ctx *ctx, int64_t n, const double *org, const double *dir, double *t, double *nrm, double *nrm_raw, int32_t *obj,
+                         int32_t *into, int32_t *prim) {
+    return intersect_impl(ctx, n, org, dir, t, nrm, nrm_raw, obj, into, prim, false, nullptr, nullptr);
+}
+int cgrt_count_traversal(cgrt_ctx *ctx, int64_t n, const double *org, const double *dir, uint64_t *node_visits, uint64_t *tri_tests) {
+    return intersect_impl(ctx, n, org, dir, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, true, node_visits, tri_tests);
+}
+
+int cgrt_hash_keys(cgrt_ctx *ctx, int64_t n, const double *pos, int hashsize, double celllength_in, uint32_t *key, int32_t *ixyz) {
+    if (!ctx || n < 0 || !pos || hashsize <= 0 || !(celllength_in > 0)) return CGRT_ERR_INVALID;
+    if (n == 0) return CGRT_OK;
+    CK(cudaSetDevice(ctx->device));
+    int cells = (int)(std::ceil(70.0 / celllength_in));  // hash.h:25-26
+    double cl = 70.0 / cells;
+    double *d_pos;
+    uint32_t *d_key;
+    int *d_ixyz;
+    CKS(upload(ctx, &d_pos, pos, (size_t)n * 3));
+    CKS(dalloc(ctx, &d_key, (size_t)n)); CKS(dalloc(ctx, &d_ixyz, (size_t)n * 3));
+    hash_keys_kernel<<<nblk(n, 256), 256, 0, ctx->stream>>>(n, d_pos, (uint32_t)hashsize, cl, d_key, d_ixyz);
+    ctx->launches++;
+    CK(cudaGetLastError());
+    CKS(download_free(ctx, key, d_key, (size_t)n));
+    CKS(download_free(ctx, (int *)ixyz, d_ixyz, (size_t)n * 3));
+    CKS(dfree(ctx, d_pos));
+    return CGRT_OK;
+}
+
+int cgrt_surface_color(cgrt_ctx *ctx, int obj, int64_t n, const double *pos, double *col) {
+    if (!ctx || n < 0 || !pos || !col) return CGRT_ERR_INVALID;
+    if (!ctx->committed || obj < 0 || obj >= ctx->S.nobj) FAIL(CGRT_ERR_INVALID, "bad object id / scene not committed");
+    if (n == 0) return CGRT_OK;
+    double *d_pos, *d_col;
+    CKS(upload(ctx, &d_pos, pos, (size_t)n * 3));
+    CKS(dalloc(ctx, &d_col, (size_t)n * 3));
+    surface_color_kernel<<<nblk(n, 256), 256, 0, ctx->stream>>>(ctx->S, obj, n, d_pos, d_col);
+    ctx->launches++;
+    CK(cudaGetLastError());
+    CKS(download_free(ctx, col, d_col, (size_t)n * 3));
+    CKS(dfree(ctx, d_pos));
+    return CGRT_OK;
+}
+
+int cgrt_object_triangles(cgrt_ctx *ctx, int obj, double *tri9, int64_t cap, int64_t *ntri) {
+    if (!ctx || !ntri) return CGRT_ERR_INVALID;
+    if (!ctx->committed || obj < 0 || obj >= ctx->S.nobj) FAIL(CGRT_ERR_INVALID, "bad object id / scene not committed");
+    int b = ctx->obj_bvh[obj];
+    *ntri = b < 0 ? 0 : ctx->bvh_src[b].ntris;
+    if (tri9 && b >= 0) {
+        int64_t n = *ntri < cap ? *ntri : cap;
+        CK(cudaMemcpy(tri9, ctx->bvh_src[b].tri9, (size_t)n * 9 * sizeof(double), cudaMemcpyDeviceToHost));
+    }
+    return CGRT_OK;
+}
+
+int cgrt_sample(cgrt_ctx *ctx, uint64_t seed, uint32_t pass, uint64_t path, uint32_t dim, int what, const double aux[3], double out[3]) {
+    if (!ctx || !out) return CGRT_ERR_INVALID;
+    double *d_out;
+    CKS(dalloc(ctx, &d_out, 3));
+    double a0 = aux ? aux[0] : 0, a1 = aux ? aux[1] : 0, a2 = aux ? aux[2] : 0;
+    sample_kernel<<<1, 1, 0, ctx->stream>>>(seed, pass, path, dim, what, a0, a1, a2, d_out);
+    ctx->launches++;
+    CK(cudaGetLastError());
+    return download_free(ctx, out, d_out, 3);
+}
+
+int cgrt_radix_sort(cgrt_ctx *ctx, int64_t n, const uint64_t *key_in, int nbits, uint64_t *key_out, uint32_t *perm) {
+    if (!ctx || n < 0 || !key_in || nbits <= 0 || nbits > 64) return CGRT_ERR_INVALID;
+    if (n == 0) return CGRT_OK;
+    uint64_t *d_in, *d_out;
+    uint32_t *d_perm;
+    CKS(upload(ctx, &d_in, key_in, (size_t)n));
+    CKS(dalloc(ctx, &d_out, (size_t)n)); CKS(dalloc(ctx, &d_perm, (size_t)n));
+    CKS(radix_sort_dev(ctx, (size_t)n, d_in, nbits, d_out, d_perm));
+    CKS(download_free(ctx, key_out, d_out, (size_t)n));
+    CKS(download_free(ctx, perm, d_perm, (size_t)n));
+    return dfree(ctx, d_in);
+}
+
+// ---- eye pass ------------------------------------------------------------------------------------------------------
+int cgrt_eye_pass(cgrt_ctx *ctx, int y0, int y1) {
+    if (!ctx) return CGRT_ERR_INVALID;
+    if (!ctx->committed) FAIL(CGRT_ERR_INVALID, "commit the scene first");
+    if (ctx->grid_built) FAIL(CGRT_ERR_INVALID, "grid already built");
+    const PassParams &P = ctx->P;
+    if (y1 < 0) y1 = P.height;
+    if (y0 < 0 || y1 > P.height || y0 >= y1) FAIL(CGRT_ERR_INVALID, "bad row range");
+    CK(cudaSetDevice(ctx->device));
+    PhaseTimer timer(ctx, 0);
+    size_t per_row = (size_t)P.width * P.samples;
+    size_t max_rays = 4u << 20;
+    int rows_per_chunk = (int)(max_rays / per_row);
+    if (rows_per_chunk < 1) rows_per_chunk = 1;
+    for (int r0 = y0; r0 < y1; r0 += rows_per_chunk) {
+        int r1 = r0 + rows_per_chunk < y1 ? r0 + rows_per_chunk : y1;
+        size_t n = (size_t)(r1 - r0) * per_row;
+        int cur = 0;
+        for (int depth = 0; depth < P.max_depth && n > 0; depth++) {
+            CKS(ensure_queues(ctx, 2 * n > ctx->photon_chunk ? 2 * n : ctx->photon_chunk));
+            CKS(ensure_hp_capacity(ctx, (size_t)ctx->hp_count + n));
+            CK(cudaMemsetAsync(ctx->d_qcount + (cur ^ 1), 0, sizeof(unsigned int), ctx->stream));
+            if (depth == 0)
+                eye_bounce_kernel<true><<<nblk(n, 128), 128, 0, ctx->stream>>>(ctx->S, P, depth, ctx->q[cur], (unsigned int)n, r0, ctx->q[cur ^ 1],
+                                                                               ctx->d_qcount + (cur ^ 1), ctx->hp_rec, ctx->d_hp_count, ctx->hp_cap, ctx->d_ctr);
+            else
+                eye_bounce_kernel<false><<<nblk(n, 128), 128, 0, ctx->stream>>>(ctx->S, P, depth, ctx->q[cur], (unsigned int)n, r0, ctx->q[cur ^ 1],
+                                                                                ctx->d_qcount + (cur ^ 1), ctx->hp_rec, ctx->d_hp_count, ctx->hp_cap, ctx->d_ctr);
+            ctx->launches++;
+            CK(cudaGetLastError());
+            unsigned int counts[2];
+            CK(cudaMemcpyAsync(&counts[0], ctx->d_qcount + (cur ^ 1), sizeof(unsigned int), cudaMemcpyDeviceToHost, ctx->stream));
+            CK(cudaMemcpyAsync(&counts[1], ctx->d_hp_count, sizeof(unsigned int), cudaMemcpyDeviceToHost, ctx->stream));
+            CK(cudaStreamSynchronize(ctx->stream));
+            n = counts[0];
+            ctx->hp_count = counts[1];
+            cur ^= 1;
+        }
+    }
+    timer.stop();
+    return CGRT_OK;
+}
+
+int cgrt_export_hitpoints_dev(cgrt_ctx *ctx, void **records_dev, int64_t *count) {
+    if (!ctx || !records_dev || !count) return CGRT_ERR_INVALID;
+    *records_dev = ctx->hp_rec;
+    *count = ctx->hp_count;
+    return CGRT_OK;
+}
+int cgrt_import_hitpoints_dev(cgrt_ctx *ctx, const void *records_dev, int64_t count) {
+    if (!ctx || count < 0 || (count > 0 && !records_dev)) return CGRT_ERR_INVALID;
+    if (ctx->grid_built) FAIL(CGRT_ERR_INVALID, "grid already built");
+    CK(cudaSetDevice(ctx->device));
+    // replaces the current set (the caller passes the all-gathered union, which includes this rank's own records)
+    ctx->hp_count = 0;
+    CKS(ensure_hp_capacity(ctx, (size_t)count));
+    if (count) CK(cudaMemcpyAsync(ctx->hp_rec, records_dev, (size_t)count * 12 * sizeof(double), cudaMemcpyDeviceToDevice, ctx->stream));
+    unsigned int c = (unsigned int)count;
+    CK(cudaMemcpyAsync(ctx->d_hp_count, &c, sizeof c, cudaMemcpyHostToDevice, ctx->stream));
+    CK(cudaStreamSynchronize(ctx->stream));
+    ctx->hp_count = c;
+    return CGRT_OK;
+}
+
+// ---- grid ----------------------------------------------------------------------------------------------------------
+int cgrt_build_grid(cgrt_ctx *ctx) {
+    if (!ctx) return CGRT_ERR_INVALID;
+    if (ctx->grid_built) FAIL(CGRT_ERR_INVALID, "grid already built");
+    CK(cudaSetDevice(ctx->device));
+    PhaseTimer timer(ctx, 1);
+    const PassParams &P = ctx->P;
+    unsigned int n = ctx->hp_count;
+    ctx->nhp = n;
+    size_t npix = (size_t)P.width * P.height;
+    CKS(dalloc(ctx, &ctx->cell_start, (size_t)P.hashsize + 1));
+    CKS(dalloc(ctx, &ctx->pix_start, npix + 1));
+    CKS(dalloc(ctx, &ctx->pix_perm, (size_t)n));
+    CKS(dalloc(ctx, &ctx->A.hot, (size_t)n));
+    CKS(dalloc(ctx, &ctx->A.f, (size_t)n * 4));
+    CKS(dalloc(ctx, &ctx->A.flux, (size_t)n * 4));
+    CKS(dalloc(ctx, &ctx->A.cnt, (size_t)n));
+    CKS(dalloc(ctx, &ctx->A.hw, (size_t)n * 2));
+    CKS(dalloc(ctx, &ctx->A.key, (size_t)n));
+    CKS(dalloc(ctx, &ctx->A.seq, (size_t)n));
+    size_t acc_bytes = (size_t)n * 4 * (ctx->cfg.accum_mode == 0 ? sizeof(double) : sizeof(float));
+    {
+        char *a;
+        CKS(dalloc(ctx, &a, acc_bytes));
+        ctx->acc = a;
+        CK(cudaMemsetAsync(a, 0, acc_bytes ? acc_bytes : 1, ctx->stream));
+    }
+    if (n > 0) {
+        uint64_t *keys, *keys_sorted, *pixkeys, *pixkeys_sorted;
+        uint32_t *perm;
+        CKS(dalloc(ctx, &keys, (size_t)n)); CKS(dalloc(ctx, &keys_sorted, (size_t)n)); CKS(dalloc(ctx, &perm, (size_t)n));
+        CKS(dalloc(ctx, &pixkeys, (size_t)n)); CKS(dalloc(ctx, &pixkeys_sorted, (size_t)n));
+        hp_extract_keys_kernel<<<nblk(n, 256), 256, 0, ctx->stream>>>(ctx->hp_rec, n, keys);
+        ctx->launches++;
+        int kbits = 32;
+        while (kbits > 1 && !(((uint64_t)P.hashsize - 1) >> (kbits - 1))) kbits--;
+        CKS(radix_sort_dev(ctx, n, keys, 32 + kbits, keys_sorted, perm));
+        hp_gather_sorted_kernel<<<nblk(n, 256), 256, 0, ctx->stream>>>(ctx->hp_rec, perm, n, P.r2_init, ctx->A, pixkeys, P.width);
+        lower_bound_table_kernel<<<nblk((size_t)n + 1, 256), 256, 0, ctx->stream>>>(ctx->A.key, nullptr, n, P.hashsize, ctx->cell_start);
+        ctx->launches += 2;
+        int pbits = 1;
+        while (pbits < 40 && ((uint64_t)npix >> pbits)) pbits++;
+        CKS(radix_sort_dev(ctx, n, pixkeys, pbits, pixkeys_sorted, ctx->pix_perm));
+        lower_bound_table_kernel<<<nblk((size_t)n + 1, 256), 256, 0, ctx->stream>>>(nullptr, pixkeys_sorted, n, (unsigned int)npix, ctx->pix_start);
+        ctx->launches++;
+        CK(cudaStreamSynchronize(ctx->stream));
+        CK(cudaGetLastError());
+        CKS(dfree(ctx, keys)); CKS(dfree(ctx, keys_sorted)); CKS(dfree(ctx, perm)); CKS(dfree(ctx, pixkeys)); CKS(dfree(ctx, pixkeys_sorted));
+    } else {
+        CK(cudaMemsetAsync(ctx->cell_start, 0, ((size_t)P.hashsize + 1) * sizeof(uint32_t), ctx->stream));
+        CK(cudaMemsetAsync(ctx->pix_start, 0, (npix + 1) * sizeof(uint32_t), ctx->stream));
+    }
+    // the raw records are no longer needed
+    CKS(dfree(ctx, ctx->hp_rec));
+    ctx->hp_rec = nullptr;
+    ctx->hp_cap = 0;
+    ctx->grid_built = true;
+    timer.stop();
+    return CGRT_OK;
+}
+
+// ---- photon pass ---------------------------------------------------------------------------------------------------
+int cgrt_photon_pass(cgrt_ctx *ctx, uint64_t first, uint64_t count) {
+    if (!ctx) return CGRT_ERR_INVALID;
+    if (!ctx->grid_built) FAIL(CGRT_ERR_INVALID, "build the grid first");
+    CK(cudaSetDevice(ctx->device));
+    const PassParams &P = ctx->P;
+    CKS(ensure_queues(ctx, ctx->photon_chunk));
+    cudaEvent_t e0, e1, e2;
+    CK(cudaEventCreate(&e0)); CK(cudaEventCreate(&e1)); CK(cudaEventCreate(&e2));
+    for (uint64_t done = 0; done < count; done += ctx->photon_chunk) {
+        size_t n = (size_t)((count - done) < ctx->photon_chunk ? (count - done) : ctx->photon_chunk);
+        uint64_t base = first + done;
+        int cur = 0;
+        for (int depth = 0; depth < P.max_depth && n > 0; depth++) {
+            CK(cudaMemsetAsync(ctx->d_qcount + (cur ^ 1), 0, sizeof(unsigned int), ctx->stream));
+            CK(cudaMemsetAsync(ctx->d_qcount + 2, 0, sizeof(unsigned int), ctx->stream));
+            CK(cudaEventRecord(e0, ctx->stream));
+            if (depth == 0)
+                photon_trace_kernel<true><<<nblk(n, 128), 128, 0, ctx->stream>>>(ctx->S, P, depth, ctx->q[cur], (unsigned int)n, base, ctx->q[cur ^ 1],
+                                                                                 ctx->d_qcount + (cur ^ 1), ctx->dq, ctx->d_qcount + 2, ctx->d_ctr);
+            else
+                photon_trace_kernel<false><<<nblk(n, 128), 128, 0, ctx->stream>>>(ctx->S, P, depth, ctx->q[cur], (unsigned int)n, base, ctx->q[cur ^ 1],
+                                                                                  ctx->d_qcount + (cur ^ 1), ctx->dq, ctx->d_qcount + 2, ctx->d_ctr);
+            ctx->launches++;
+            CK(cudaEventRecord(e1, ctx->stream));
+            unsigned int counts[2];
+            CK(cudaMemcpyAsync(&counts[0], ctx->d_qcount + (cur ^ 1), sizeof(unsigned int), cudaMemcpyDeviceToHost, ctx->stream));
+            CK(cudaMemcpyAsync(&counts[1], ctx->d_qcount + 2, sizeof(unsigned int), cudaMemcpyDeviceToHost, ctx->stream));
+            CK(cudaStreamSynchronize(ctx->stream));
+            CK(cudaGetLastError());
+            unsigned int ndq = counts[1];
+            if (ndq > 0 && ctx->nhp > 0) {
+                unsigned int blocks = nblk((size_t)ndq * 32, 256);
+                unsigned int maxb = 148 * 8 * 4;
+                if (blocks > maxb) blocks = maxb;
+                if (ctx->cfg.accum_mode == 0)
+                    photon_deposit_kernel<0><<<blocks, 256, 0, ctx->stream>>>(P, ctx->dq, ndq, ctx->cell_start, ctx->A.hot, ctx->A.f, ctx->acc, ctx->d_ctr);
+                else
+                    photon_deposit_kernel<1><<<blocks, 256, 0, ctx->stream>>>(P, ctx->dq, ndq, ctx->cell_start, ctx->A.hot, ctx->A.f, ctx->acc, ctx->d_ctr);
+                ctx->launches++;
+            }
+            CK(cudaEventRecord(e2, ctx->stream));
+            CK(cudaEventSynchronize(e2));
+            CK(cudaGetLastError());
+            float t01 = 0, t12 = 0;
+            cudaEventElapsedTime(&t01, e0, e1);
+            cudaEventElapsedTime(&t12, e1, e2);
+            ctx->ms[2] += t01;
+            ctx->ms[3] += t12;
+            ctx->diffuse_hits += ndq;  // every queued deposit is one diffuse photon hit (main.cpp:101)
+            n = counts[0];
+            cur ^= 1;
+        }
+    }
+    cudaEventDestroy(e0); cudaEventDestroy(e1); cudaEventDestroy(e2);
+    return CGRT_OK;
+}
+
+int cgrt_accum_dev(cgrt_ctx *ctx, void **ptr_dev, int64_t *n_elems) {
+    if (!ctx || !ptr_dev || !n_elems) return CGRT_ERR_INVALID;
+    if (!ctx->grid_built) FAIL(CGRT_ERR_INVALID, "build the grid first");
+    *ptr_dev = ctx->acc;
+    *n_elems = (int64_t)ctx->nhp * 4;
+    return CGRT_OK;
+}
+
+int cgrt_allreduce_accum(cgrt_ctx *ctx, void *nccl_comm) {
+    if (!ctx) return CGRT_ERR_INVALID;
+    if (!nccl_comm) return CGRT_OK;
+#ifdef CGRT_WITH_NCCL
+    if (!ctx->grid_built) FAIL(CGRT_ERR_INVALID, "build the grid first");
+    ncclResult_t r = ncclAllReduce(ctx->acc, ctx->acc, (size_t)ctx->nhp * 4, ctx->cfg.accum_mode == 0 ? ncclDouble : ncclFloat, ncclSum,
+                                   (ncclComm_t)nccl_comm, ctx->stream);
+    if (r != ncclSuccess) FAIL(CGRT_ERR_NCCL, ncclGetErrorString(r));
+    CK(cudaStreamSynchronize(ctx->stream));
+    return CGRT_OK;
+#else
+    FAIL(CGRT_ERR_NCCL, "libcgrt.so was built without NCCL; all-reduce the cgrt_accum_dev buffer from the host framework instead");
+#endif
+}
+
+int cgrt_round_update(cgrt_ctx *ctx) {
+    if (!ctx) return CGRT_ERR_INVALID;
+    if (!ctx->grid_built) FAIL(CGRT_ERR_INVALID, "build the grid first");
+    CK(cudaSetDevice(ctx->device));
+    PhaseTimer timer(ctx, 4);
+    unsigned int n = ctx->nhp;
+    if (n > 0) {
+        if (ctx->cfg.accum_mode == 0) round_update_kernel<0><<<nblk(n, 256), 256, 0, ctx->stream>>>(n, ctx->P.alpha, ctx->A, ctx->acc);
+        else round_update_kernel<1><<<nblk(n, 256), 256, 0, ctx->stream>>>(n, ctx->P.alpha, ctx->A, ctx->acc);
+        ctx->launches++;
+        CK(cudaGetLastError());
+    }
+    timer.stop();
+    return CGRT_OK;
+}
+
+int cgrt_gather_image(cgrt_ctx *ctx, double n_emitted, double *rgb, uint8_t *rgb8) {
+    if (!ctx || !rgb) return CGRT_ERR_INVALID;
+    if (!ctx->grid_built) FAIL(CGRT_ERR_INVALID, "build the grid first");
+    CK(cudaSetDevice(ctx->device));
+    PhaseTimer timer(ctx, 5);
+    const PassParams &P = ctx->P;
+    size_t npix = (size_t)P.width * P.height;
+    double *d_rgb;
+    uint8_t *d_rgb8 = nullptr;
+    CKS(dalloc(ctx, &d_rgb, npix * 3));
+    if (rgb8) CKS(dalloc(ctx, &d_rgb8, npix * 3));
+    image_gather_kernel<<<nblk(npix, 256), 256, 0, ctx->stream>>>(P.width, P.height, n_emitted, ctx->pix_start, ctx->pix_perm, ctx->A.hot, ctx->A.flux,
+                                                                  d_rgb, d_rgb8);
+    ctx->launches++;
+    CK(cudaGetLastError());
+    CKS(download_free(ctx, rgb, d_rgb, npix * 3));
+    if (rgb8) CKS(download_free(ctx, rgb8, d_rgb8, npix * 3));
+    timer.stop();
+    return CGRT_OK;
+}
+
+// ---- downloads -----------------------------------------------------------------------------------------------------
+int cgrt_num_hitpoints(cgrt_ctx *ctx, int64_t *n) {
+    if (!ctx || !n) return CGRT_ERR_INVALID;
+    *n = ctx->grid_built ? ctx->nhp : ctx->hp_count;
+    return CGRT_OK;
+}
+
+int cgrt_download_hitpoints(cgrt_ctx *ctx, double *pos, double *normal, double *f, double *flux, double *r2, int32_t *n, int32_t *hw, uint32_t *key,
+                            uint32_t *seq) {
+    if (!ctx) return CGRT_ERR_INVALID;
+    if (!ctx->grid_built) FAIL(CGRT_ERR_INVALID, "build the grid first");
+    size_t m = ctx->nhp;
+    if (m == 0) return CGRT_OK;
+    std::vector<HpHot> hot(m);
+    std::vector<double> tmp(m * 4);
+    CK(cudaMemcpy(hot.data(), ctx->A.hot, m * sizeof(HpHot), cudaMemcpyDeviceToHost));
+    for (size_t i = 0; i < m; i++) {
+        if (pos) { pos[3 * i] = hot[i].px; pos[3 * i + 1] = hot[i].py; pos[3 * i + 2] = hot[i].pz; }
+        if (normal) { normal[3 * i] = hot[i].nx; normal[3 * i + 1] = hot[i].ny; normal[3 * i + 2] = hot[i].nz; }
+        if (r2) r2[i] = hot[i].r2;
+    }
+    if (f) {
+        CK(cudaMemcpy(tmp.data(), ctx->A.f, m * 4 * sizeof(double), cudaMemcpyDeviceToHost));
+        for (size_t i = 0; i < m; i++) { f[3 * i] = tmp[4 * i]; f[3 * i + 1] = tmp[4 * i + 1]; f[3 * i + 2] = tmp[4 * i + 2]; }
+    }
+    if (flux) {
+        CK(cudaMemcpy(tmp.data(), ctx->A.flux, m * 4 * sizeof(double), cudaMemcpyDeviceToHost));
+        for (size_t i = 0; i < m; i++) { flux[3 * i] = tmp[4 * i]; flux[3 * i + 1] = tmp[4 * i + 1]; flux[3 * i + 2] = tmp[4 * i + 2]; }
+    }
+    if (n) CK(cudaMemcpy(n, ctx->A.cnt, m * sizeof(int), cudaMemcpyDeviceToHost));
+    if (hw) CK(cudaMemcpy(hw, ctx->A.hw, m * 2 * sizeof(int), cudaMemcpyDeviceToHost));
+    if (key) CK(cudaMemcpy(key, ctx->A.key, m * sizeof(uint32_t), cudaMemcpyDeviceToHost));
+    if (seq) CK(cudaMemcpy(seq, ctx->A.seq, m * sizeof(uint32_t), cudaMemcpyDeviceToHost));
+    return CGRT_OK;
+}
+
+int cgrt_download_accum(cgrt_ctx *ctx, double *dflux, double *mcount) {
+    if (!ctx) return CGRT_ERR_INVALID;
+    if (!ctx->grid_built) FAIL(CGRT_ERR_INVALID, "build the grid first");
+    size_t m = ctx->nhp;
+    if (m == 0) return CGRT_OK;
+    CK(cudaStreamSynchronize(ctx->stream));
+    if (ctx->cfg.accum_mode == 0) {
+        std::vector<double> a(m * 4);
+        CK(cudaMemcpy(a.data(), ctx->acc, m * 4 * sizeof(double), cudaMemcpyDeviceToHost));
+        for (size_t i = 0; i < m; i++) {
+            if (dflux) { dflux[3 * i] = a[4 * i]; dflux[3 * i + 1] = a[4 * i + 1]; dflux[3 * i + 2] = a[4 * i + 2]; }
+            if (mcount) mcount[i] = a[4 * i + 3];
+        }
+    } else {
+        std::vector<float> a(m * 4);
+        CK(cudaMemcpy(a.data(), ctx->acc, m * 4 * sizeof(float), cudaMemcpyDeviceToHost));
+        for (size_t i = 0; i < m; i++) {
+            if (dflux) { dflux[3 * i] = a[4 * i]; dflux[3 * i + 1] = a[4 * i + 1]; dflux[3 * i + 2] = a[4 * i + 2]; }
+            if (mcount) mcount[i] = a[4 * i + 3];
+        }
+    }
+    return CGRT_OK;
+}
+
+int cgrt_download_grid(cgrt_ctx *ctx, uint32_t *cell_start) {
+    if (!ctx || !cell_start) return CGRT_ERR_INVALID;
+    if (!ctx->grid_built) FAIL(CGRT_ERR_INVALID, "build the grid first");
+    CK(cudaMemcpy(cell_start, ctx->cell_start, ((size_t)ctx->P.hashsize + 1) * sizeof(uint32_t), cudaMemcpyDeviceToHost));
+    return CGRT_OK;
+}
+
+int cgrt_get_counters(cgrt_ctx *ctx, cgrt_counters *out) {
+    if (!ctx || !out) return CGRT_ERR_INVALID;
+    Counters c;
+    CK(cudaStreamSynchronize(ctx->stream));
+    CK(cudaMemcpy(&c, ctx->d_ctr, sizeof c, cudaMemcpyDeviceToHost));
+    memset(out, 0, sizeof *out);
+    out->eye_segments = c.eye_segments;
+    out->photon_segments = c.photon_segments;
+    out->diffuse_hits = ctx->diffuse_hits;
+    out->candidates = c.candidates;
+    out->deposits = c.deposits;
+    out->hitpoints = ctx->grid_built ? ctx->nhp : ctx->hp_count;
+    out->gpu_launches = ctx->launches;
+    return CGRT_OK;
+}
+
+int cgrt_get_timings(cgrt_ctx *ctx, double ms[8]) {
+    if (!ctx || !ms) return CGRT_ERR_INVALID;
+    for (int i = 0; i < 8; i++) ms[i] = ctx->ms[i];
+    return CGRT_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,542 @@
+// cgrt_device.cuh — device-side building blocks of the photon-mapping hot path (sm_100a).
+//
+// Arithmetic policy: everything that decides a hit, a position, a cell key or an accept/reject is IEEE fp64 in the
+// reference's own operation order (compiled with -fmad=false, so no contraction), which makes the GPU path replay the
+// CPU oracle bit for bit. B200 keeps full-rate FP64 vector units (unlike B300), which is what makes this affordable.
+// Only the BVH box test is free-form (explicit fma, padded float bounds): it is conservative, never decisive.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+namespace cgrt {
+
+// ---------------------------------------------------------------------------------------------------------------
+// vec3.h:11-92 as a POD
+// ---------------------------------------------------------------------------------------------------------------
+struct d3 {
+    double x, y, z;
+};
+__host__ __device__ __forceinline__ d3 mk(double x, double y, double z) { d3 r; r.x = x; r.y = y; r.z = z; return r; }
+__host__ __device__ __forceinline__ d3 operator+(d3 a, d3 b) { return mk(a.x + b.x, a.y + b.y, a.z + b.z); }
+__host__ __device__ __forceinline__ d3 operator-(d3 a, d3 b) { return mk(a.x - b.x, a.y - b.y, a.z - b.z); }
+__host__ __device__ __forceinline__ d3 operator-(d3 a) { return mk(-a.x, -a.y, -a.z); }
+__host__ __device__ __forceinline__ d3 operator*(d3 a, double f) { return mk(a.x * f, a.y * f, a.z * f); }   // vec3.h:50
+__host__ __device__ __forceinline__ d3 operator*(d3 a, d3 b) { return mk(a.x * b.x, a.y * b.y, a.z * b.z); } // vec3.h:54
+__host__ __device__ __forceinline__ double dot(d3 a, d3 b) { return a.x * b.x + a.y * b.y + a.z * b.z; }     // vec3.h:61
+__host__ __device__ __forceinline__ d3 cross(d3 a, d3 b) {                                                   // vec3.h:81
+    return mk(a.y * b.z - a.z * b.y, a.z * b.x - a.x * b.z, a.x * b.y - a.y * b.x);
+}
+__host__ __device__ __forceinline__ d3 normalize(d3 a) {  // vec3.h:35-43: multiply by (1/len), three times
+    double len = sqrt(a.x * a.x + a.y * a.y + a.z * a.z);
+    if (len > 0) {
+        a.x *= 1 / len;
+        a.y *= 1 / len;
+        a.z *= 1 / len;
+    }
+    return a;
+}
+// vec3.h:95-97, strictly left to right
+__host__ __device__ __forceinline__ double det3(d3 a, d3 b, d3 c) {
+    return (a.x * b.y * c.z + b.x * c.y * a.z + c.x * a.y * b.z - a.x * c.y * b.z - b.x * a.y * c.z - c.x * b.y * a.z);
+}
+// util.h:16-26
+__host__ __device__ __forceinline__ double max3(double a, double b, double c) {
+    if (a > b && a > c) return a;
+    else if (b > c) return b;
+    else return c;
+}
+
+#define CGRT_EPS 1e-4               /* main.cpp:24 */
+#define CGRT_INF 1e10               /* main.cpp:25, objects.h:15 */
+#define CGRT_PI 3.14159265358979    /* main.cpp:26 */
+
+// ---------------------------------------------------------------------------------------------------------------
+// Philox4x32-10 counter RNG (replaces rand(), sampling.h). key = {seed_lo, seed_hi + pass},
+// counter = {path_lo, path_hi, dim, block}; u = (double)(word >> 1) / 2147483647.0 (the rand()/RAND_MAX lattice).
+// ---------------------------------------------------------------------------------------------------------------
+enum { PASS_EYE = 0, PASS_PHOTON = 1, PASS_BEZIER = 2 };
+
+struct Philox {
+    uint32_t k0, k1, c0, c1, c2, c3;
+    uint32_t buf[4];
+    int idx;
+    __host__ __device__ __forceinline__ void init(uint64_t seed, uint32_t pass, uint64_t path, uint32_t dim) {
+        k0 = (uint32_t)seed;
+        k1 = (uint32_t)(seed >> 32) + pass;
+        c0 = (uint32_t)path;
+        c1 = (uint32_t)(path >> 32);
+        c2 = dim;
+        c3 = 0;
+        idx = 4;
+    }
+    __host__ __device__ __forceinline__ void block() {
+        uint32_t a0 = c0, a1 = c1, a2 = c2, a3 = c3, x0 = k0, x1 = k1;
+#pragma unroll
+        for (int r = 0; r < 10; r++) {
+#ifdef __CUDA_ARCH__
+            uint32_t h0 = __umulhi(0xD2511F53u, a0), l0 = 0xD2511F53u * a0;
+            uint32_t h1 = __umulhi(0xCD9E8D57u, a2), l1 = 0xCD9E8D57u * a2;
+#else
+            uint64_t p0 = (uint64_t)0xD2511F53u * a0, p1 = (uint64_t)0xCD9E8D57u * a2;
+            uint32_t h0 = (uint32_t)(p0 >> 32), l0 = (uint32_t)p0, h1 = (uint32_t)(p1 >> 32), l1 = (uint32_t)p1;
+#endif
+            uint32_t n0 = h1 ^ a1 ^ x0, n2 = h0 ^ a3 ^ x1;
+            a0 = n0; a1 = l1; a2 = n2; a3 = l0;
+            x0 += 0x9E3779B9u;
+            x1 += 0xBB67AE85u;
+        }
+        buf[0] = a0; buf[1] = a1; buf[2] = a2; buf[3] = a3;
+        c3++;
+        idx = 0;
+    }
+    __host__ __device__ __forceinline__ double u01() {
+        if (idx == 4) block();
+        uint32_t w = buf[0];
+        // select without dynamic local-memory indexing
+        w = idx == 1 ? buf[1] : w;
+        w = idx == 2 ? buf[2] : w;
+        w = idx == 3 ? buf[3] : w;
+        idx++;
+        return (double)(w >> 1) / 2147483647.0;
+    }
+};
+
+#define CGRT_MAX_REJECT 64
+// sampling.h:11-20
+__host__ __device__ __forceinline__ d3 sample_sphere(Philox &g) {
+    d3 v = mk(0, 0, 0);
+    for (int it = 0; it < CGRT_MAX_REJECT; it++) {
+        double x = g.u01() * 2.0 - 1;
+        double y = g.u01() * 2.0 - 1;
+        double z = g.u01() * 2.0 - 1;
+        v = mk(x, y, z);
+        if (x * x + y * y + z * z <= 1) break;
+    }
+    return normalize(v);
+}
+// sampling.h:22-29
+__host__ __device__ __forceinline__ d3 sample_halfsphere(Philox &g, d3 dir) {
+    d3 s = mk(0, 0, 0);
+    for (int it = 0; it < CGRT_MAX_REJECT; it++) {
+        s = sample_sphere(g);
+        if (dot(s, dir) > 0) break;
+    }
+    return s;
+}
+// sampling.h:35-43
+__host__ __device__ __forceinline__ d3 sample_circle(Philox &g, double radius) {
+    double x = 0, y = 0;
+    for (int it = 0; it < CGRT_MAX_REJECT; it++) {
+        x = g.u01() * 2.0 - 1;
+        y = g.u01() * 2.0 - 1;
+        if (x * x + y * y < 1) break;
+    }
+    return mk(x, y, 0) * radius;
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// Device scene (passed to kernels by value as a __grid_constant__ parameter: uniform constant-bank reads)
+// ---------------------------------------------------------------------------------------------------------------
+enum { OBJ_SPHERE = 0, OBJ_PLANE = 1, OBJ_MESH = 2, OBJ_BEZIER = 3 };
+enum { MAT_DIFFUSE = 0, MAT_MIRROR = 1, MAT_GLASS = 2 };  // main.cpp:82,129,135 thresholds
+
+#define CGRT_MAX_OBJECTS 12
+#define CGRT_MAX_BVH 4
+#define CGRT_MAX_TEX 4
+#define CGRT_MAX_BEZIER 2
+#define CGRT_MAX_CP 7
+
+// One BVH2 node, 64 bytes = two 32-byte sectors: both children's boxes (float, rounded outward + padded) and links.
+// child >= 0: internal node index; child < 0: leaf, ~child = index into the Morton-sorted triangle array.
+struct __align__(16) BvhNode {
+    float lo0[3], hi0[3];
+    float lo1[3], hi1[3];
+    int c0, c1;
+    int pad0, pad1;
+};
+// One triangle, 96 bytes = three sectors: pa and the edges / normal exactly as Triangle::intersect forms them
+// (objects.h:98-99,107): e1 = pa - pb, e2 = pa - pc, n = normalize(e1 x e2).
+struct __align__(16) TriRec {
+    double pa[3], e1[3], e2[3], n[3];
+};
+
+struct ObjDev {
+    int kind, material, tex, bvh, objtype, aux;
+    double a[3];      // sphere centre | plane position
+    double b[3];      // plane normal
+    double r, r2;     // sphere radius, radius*radius (objects.h:35)
+    double col[3];
+    double refl, transp;
+};
+struct BvhDev {
+    const BvhNode *nodes;
+    const TriRec *tris;
+    const int *tri_id;      // sorted position -> original triangle index
+    int ntris;
+    int root_is_leaf;
+    double orient_sign;     // winding normal * orient_sign points out of the solid
+};
+struct TexDev {
+    const uchar4 *texels;   // row-major [H][W], texel = byte/256 (main.cpp:307-311)
+    int W, H, isbump, pad;
+    double n[3], p[3], lenx, leny;
+};
+struct BezDev {
+    int ncp, pad;
+    double cp[CGRT_MAX_CP][3];
+    double pos[3];
+    double box[6];          // xmax,xmin,ymax,ymin,zmax,zmin (bezier.h:64-69)
+    double umin_r2;         // cap radius^2 = cp[last].z^2 (bezier.h:277)
+};
+struct SceneDev {
+    int nobj, nbvh, ntex, nbez;
+    ObjDev obj[CGRT_MAX_OBJECTS];
+    BvhDev bvh[CGRT_MAX_BVH];
+    TexDev tex[CGRT_MAX_TEX];
+    BezDev bez[CGRT_MAX_BEZIER];
+};
+
+struct Hit {
+    double t;
+    d3 n;        // raw normal as Object::intersect returns it
+    int obj;
+    int prim;    // original triangle index or -1
+};
+
+struct TravCounters {
+    unsigned long long node_visits, tri_tests;
+};
+
+// ---------------------------------------------------------------------------------------------------------------
+// Triangle::intersect, objects.h:96-111. The reference evaluates four quotients det_k/det1 and compares them with
+// 0 and 1; the same decisions are taken here from signs and one comparison (exactly equivalent for finite inputs
+// whose quotients do not underflow), and the only division performed is the one that produces t.
+// ---------------------------------------------------------------------------------------------------------------
+__device__ __forceinline__ bool tri_intersect(const TriRec &T, d3 o, d3 d, double &t) {
+    d3 pa = mk(T.pa[0], T.pa[1], T.pa[2]);
+    d3 e1 = mk(T.e1[0], T.e1[1], T.e1[2]);
+    d3 e2 = mk(T.e2[0], T.e2[1], T.e2[2]);
+    d3 s = pa - o;
+    double det1 = det3(d, e1, e2);
+    if (det1 == 0.0 || det1 != det1) return false;  // x/0 -> inf/nan never satisfies all four tests
+    double det3v = det3(d, s, e2);
+    double det4v = det3(d, e1, s);
+    bool pos = det1 > 0.0;
+    // det3/det1 >= 0  <=>  det3 == 0 or sign(det3) == sign(det1)
+    if (!(det3v == 0.0 || ((det3v > 0.0) == pos))) return false;
+    if (!(det4v == 0.0 || ((det4v > 0.0) == pos))) return false;
+    // (det3+det4)/det1 <= 1  <=>  det3+det4 <= det1 (det1 > 0)  |  >= det1 (det1 < 0): RN division is monotone and
+    // q(x,x) = 1 exactly, q(x',x) > 1 + 2^-53 for the next double x' > x.
+    double sum = det3v + det4v;
+    if (pos ? !(sum <= det1) : !(sum >= det1)) return false;
+    double det2 = det3(s, e1, e2);
+    double q = det2 / det1;
+    if (!(q > 0.0)) return false;
+    t = q;
+    return true;
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// BVH traversal: closest triangle with t < tmax (strict), t > 0. Stack in local memory (depth <= 64).
+// Box test: slab test in fp64 on padded float bounds with explicit fma; NaNs (0 * inf) are dropped by fmin/fmax.
+// ---------------------------------------------------------------------------------------------------------------
+__device__ __forceinline__ bool slab(const float *lo, const float *hi, d3 o, d3 id, double tmax, double &tnear) {
+    double tx0 = ((double)lo[0] - o.x) * id.x, tx1 = ((double)hi[0] - o.x) * id.x;
+    double ty0 = ((double)lo[1] - o.y) * id.y, ty1 = ((double)hi[1] - o.y) * id.y;
+    double tz0 = ((double)lo[2] - o.z) * id.z, tz1 = ((double)hi[2] - o.z) * id.z;
+    double tn = fmax(fmax(fmin(tx0, tx1), fmin(ty0, ty1)), fmax(fmin(tz0, tz1), 0.0));
+    double tf = fmin(fmin(fmax(tx0, tx1), fmax(ty0, ty1)), fmin(fmax(tz0, tz1), tmax));
+    tnear = tn;
+    return tn <= tf;
+}
+
+template <bool COUNT>
+__device__ __forceinline__ bool bvh_closest(const BvhDev &B, d3 o, d3 d, double tmax, double &t_out, int &leaf_out, TravCounters *tc) {
+    d3 id = mk(1.0 / d.x, 1.0 / d.y, 1.0 / d.z);
+    double best = tmax;
+    int best_leaf = -1;
+    int stack[64];
+    int sp = 0;
+    int node = B.root_is_leaf ? ~0 : 0;
+    for (;;) {
+        if (node >= 0) {
+            const BvhNode *np = B.nodes + node;
+            // 64 bytes as four 16-byte loads
+            const float4 *q = reinterpret_cast<const float4 *>(np);
+            float4 q0 = __ldg(q), q1 = __ldg(q + 1), q2 = __ldg(q + 2), q3 = __ldg(q + 3);
+            if (COUNT) tc->node_visits++;
+            float lo0[3] = {q0.x, q0.y, q0.z}, hi0[3] = {q0.w, q1.x, q1.y};
+            float lo1[3] = {q1.z, q1.w, q2.x}, hi1[3] = {q2.y, q2.z, q2.w};
+            int c0 = __float_as_int(q3.x), c1 = __float_as_int(q3.y);
+            double tn0, tn1;
+            bool h0 = slab(lo0, hi0, o, id, best, tn0);
+            bool h1 = slab(lo1, hi1, o, id, best, tn1);
+            if (h0 && h1) {
+                if (tn1 < tn0) { int tmp = c0; c0 = c1; c1 = tmp; }
+                stack[sp++] = c1;
+                node = c0;
+            } else if (h0) {
+                node = c0;
+            } else if (h1) {
+                node = c1;
+            } else {
+                if (sp == 0) break;
+                node = stack[--sp];
+            }
+        } else {
+            int leaf = ~node;
+            if (COUNT) tc->tri_tests++;
+            double t;
+            if (tri_intersect(B.tris[leaf], o, d, t) && t < best) {
+                best = t;
+                best_leaf = leaf;
+            }
+            if (sp == 0) break;
+            node = stack[--sp];
+        }
+    }
+    t_out = best;
+    leaf_out = best_leaf;
+    return best_leaf >= 0;
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// Bezier surface of revolution (bezier.h). The reference solves F(t,u,theta)=0 by Newton from 10 random starts;
+// here the same Newton iteration (same F, same Jacobian, same acceptance test) is started from a deterministic
+// seed grid, and the nearest accepted root is kept (parity for this primitive is statistical).
+// ---------------------------------------------------------------------------------------------------------------
+__device__ __forceinline__ bool box_any_face_hit(const double *b, d3 o, d3 d) {  // bezier.h:72-126, objects.h:166-200
+    const double e = 1e-4;
+    double xmax = b[0], xmin = b[1], ymax = b[2], ymin = b[3], zmax = b[4], zmin = b[5];
+    double t; d3 p;
+    t = (xmax - o.x) / d.x; p = o + d * t;
+    if (t > 0 && p.y >= ymin - e && p.y <= ymax + e && p.z >= zmin - e && p.z <= zmax + e) return true;
+    t = (xmin - o.x) / d.x; p = o + d * t;
+    if (t > 0 && p.y >= ymin - e && p.y <= ymax + e && p.z >= zmin - e && p.z <= zmax + e) return true;
+    t = (ymax - o.y) / d.y; p = o + d * t;
+    if (t > 0 && p.x >= xmin - e && p.x <= xmax + e && p.z >= zmin - e && p.z <= zmax + e) return true;
+    t = (ymin - o.y) / d.y; p = o + d * t;
+    if (t > 0 && p.x >= xmin - e && p.x <= xmax + e && p.z >= zmin - e && p.z <= zmax + e) return true;
+    t = (zmax - o.z) / d.z; p = o + d * t;
+    if (t > 0 && p.x >= xmin - e && p.x <= xmax + e && p.y >= ymin - e && p.y <= ymax + e) return true;
+    t = (zmin - o.z) / d.z; p = o + d * t;
+    if (t > 0 && p.x >= xmin - e && p.x <= xmax + e && p.y >= ymin - e && p.y <= ymax + e) return true;
+    return false;
+}
+
+// Bernstein value and derivative of the profile curve (bezier.h:30-40,127-142) by de Casteljau-free direct powers.
+__device__ __forceinline__ void bez_eval(const BezDev &Z, double u, d3 &P, d3 &dP) {
+    int n = Z.ncp - 1;
+    // binomial row
+    double C[CGRT_MAX_CP];
+    C[0] = 1.0;
+    for (int i = 1; i <= n; i++) C[i] = C[i - 1] * (double)(n - i + 1) / (double)i;
+    double pu[CGRT_MAX_CP], pv[CGRT_MAX_CP];
+    pu[0] = 1.0; pv[0] = 1.0;
+    for (int i = 1; i <= n; i++) { pu[i] = pu[i - 1] * u; pv[i] = pv[i - 1] * (1.0 - u); }
+    P = mk(0, 0, 0); dP = mk(0, 0, 0);
+    for (int i = 0; i <= n; i++) {
+        double b = C[i] * pv[n - i] * pu[i];
+        // d/du [u^i (1-u)^(n-i)] = i u^(i-1) (1-u)^(n-i) - (n-i) u^i (1-u)^(n-i-1)
+        double db = 0.0;
+        if (i > 0) db += C[i] * (double)i * pu[i - 1] * pv[n - i];
+        if (i < n) db -= C[i] * (double)(n - i) * pu[i] * pv[n - i - 1];
+        d3 c = mk(Z.cp[i][0], Z.cp[i][1], Z.cp[i][2]);
+        P = P + c * b;
+        dP = dP + c * db;
+    }
+}
+
+__device__ __forceinline__ d3 bez_F(const BezDev &Z, d3 par, d3 o, d3 d, d3 &P, d3 &dP) {  // bezier.h:144-149
+    bez_eval(Z, par.y, P, dP);
+    double s, c;
+    sincos(par.z, &s, &c);
+    d3 surf = mk(P.z * s, P.y, P.z * c);
+    return o + d * par.x - mk(Z.pos[0], Z.pos[1], Z.pos[2]) - surf;
+}
+
+__device__ bool bezier_intersect(const BezDev &Z, d3 o, d3 d, double &len, d3 &nrm) {
+    if (!box_any_face_hit(Z.box, o, d)) return false;
+    bool flag = false;
+    len = CGRT_INF;
+    d3 pos = mk(Z.pos[0], Z.pos[1], Z.pos[2]);
+    // Entry/exit of the ray through the bounding cylinder's slab gives the t range worth seeding.
+    // Seeds: 4 values of u x 3 values of t across [tlo, thi] (theta from the seed point, bezier.h:243-247).
+    double rmax = Z.box[0] - Z.pos[0];
+    double tc = dot(pos - o, d);           // closest approach to the axis point
+    double tlo = fmax(tc - 2.0 * rmax - (Z.box[2] - Z.box[3]), 0.0), thi = tc + 2.0 * rmax + (Z.box[2] - Z.box[3]);
+    for (int iu = 0; iu < 4; iu++) {
+        for (int it = 0; it < 4; it++) {
+            double u0 = (iu + 0.5) * 0.25;
+            double t0 = tlo + (thi - tlo) * (it + 0.5) * 0.25;
+            d3 pt = o + d * t0 - pos;
+            double theta = (pt.z < 0) ? 3.14159265 + atan(pt.x / pt.z) : atan(pt.x / pt.z);
+            d3 par = mk(t0, u0, theta);
+            d3 P, dP;
+            d3 F = bez_F(Z, par, o, d, P, dP);
+            int iter = 0;
+            while (sqrt(dot(F, F)) > 1e-6 && iter < 100) {  // bezier.h:170
+                iter++;
+                double s, c;
+                sincos(par.z, &s, &c);
+                // Jacobian columns (bezier.h:150-162)
+                d3 a = d;
+                d3 b = mk(-s * dP.z, -dP.y, -c * dP.z);
+                d3 cc = mk(-c * P.z, 0.0, s * P.z);
+                double D = det3(a, b, cc);
+                if (D < 1e-4 && D > -1e-4) {  // vec3.h:105: singular -> the reference jitters; we nudge deterministically
+                    par = mk(par.x + 0.037, par.y + 0.029 * ((iter & 1) ? 1 : -1), par.z + 0.041);
+                    F = bez_F(Z, par, o, d, P, dP);
+                    continue;
+                }
+                // inverse (vec3.h:109-117) applied to F (vec3.h:99-101)
+                d3 ra = mk((b.y * cc.z - b.z * cc.y) / D, (cc.y * a.z - cc.z * a.y) / D, (a.y * b.z - a.z * b.y) / D);
+                d3 rb = mk((cc.x * b.z - cc.z * b.x) / D, (a.x * cc.z - a.z * cc.x) / D, (b.x * a.z - b.z * a.x) / D);
+                d3 rc = mk((b.x * cc.y - cc.x * b.y) / D, (cc.x * a.y - cc.y * a.x) / D, (a.x * b.y - a.y * b.x) / D);
+                d3 step = ra * F.x + rb * F.y + rc * F.z;
+                par = par - step;
+                F = bez_F(Z, par, o, d, P, dP);
+            }
+            if (sqrt(dot(F, F)) < 1e-4 && par.x > 0 && par.y <= 1 && par.y >= 0) {  // bezier.h:257
+                if (par.x < len) {
+                    len = par.x;
+                    // bezier.h:215-224
+                    d3 g = normalize(dP);
+                    double s, c;
+                    sincos(par.z, &s, &c);
+                    nrm = mk(g.y * s, -g.z, g.y * c);
+                    flag = true;
+                }
+            }
+        }
+    }
+    nrm = nrm * ((dot(nrm, d) < 0) ? 1.0 : -1.0);  // bezier.h:272
+    double newt = Z.box[2] - o.y;                  // bezier.h:273-281 top cap
+    if (newt > 0.1) {
+        newt = newt / d.y;
+        d3 np = o + d * newt;
+        if ((np.x - pos.x) * (np.x - pos.x) + (np.z - pos.z) * (np.z - pos.z) <= Z.umin_r2) {
+            len = newt;
+            nrm = mk(0, 1, 0);
+        }
+    }
+    return flag;
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// The closest-hit loop of trace(), main.cpp:50-63: objects in insertion order, strict <, nearest starts at INF.
+// Because acceptance is `len < nearest`, a mesh may be traversed with tmax = nearest without changing the result.
+// ---------------------------------------------------------------------------------------------------------------
+template <bool COUNT>
+__device__ __forceinline__ bool closest_hit(const SceneDev &S, d3 o, d3 d, Hit &h, TravCounters *tc) {
+    double nearest = CGRT_INF;
+    int id = -1, prim = -1;
+    d3 nrm = mk(0, 0, 0);
+    for (int i = 0; i < S.nobj; i++) {
+        const ObjDev &O = S.obj[i];
+        if (O.kind == OBJ_PLANE) {  // objects.h:505-524
+            d3 n = mk(O.b[0], O.b[1], O.b[2]);
+            d3 dd = mk(O.a[0], O.a[1], O.a[2]) - o;
+            double len = dot(dd, n) / dot(d, n);
+            if (len > 0) {
+                d3 nv = n;
+                int pr = -1;
+                if (O.bvh >= 0) {
+                    // bump height-field: accepted iff 0 < lenp < len (:514); it can only matter if it also beats nearest
+                    double lenp; int leaf;
+                    double lim = len < nearest ? len : nearest;
+                    if (bvh_closest<COUNT>(S.bvh[O.bvh], o, d, lim, lenp, leaf, tc)) {
+                        len = lenp;
+                        const TriRec &T = S.bvh[O.bvh].tris[leaf];
+                        nv = mk(T.n[0], T.n[1], T.n[2]) * S.bvh[O.bvh].orient_sign;
+                        pr = S.bvh[O.bvh].tri_id[leaf];
+                    }
+                }
+                if (len < nearest) { id = i; nearest = len; nrm = nv; prim = pr; }
+            }
+        } else if (O.kind == OBJ_MESH) {  // objects.h:405-455 -> KDTree::intersect :318-332
+            double len; int leaf;
+            const BvhDev &B = S.bvh[O.bvh];
+            if (bvh_closest<COUNT>(B, o, d, nearest, len, leaf, tc)) {
+                const TriRec &T = B.tris[leaf];
+                d3 nv = mk(T.n[0], T.n[1], T.n[2]) * B.orient_sign;
+                if (O.objtype == 2) nv = nv * ((nv.y > 0) ? 1.0 : -1.0);  // objects.h:434-436: dot with (0,1,0) is nv.y + 0 + 0
+                id = i; nearest = len; nrm = nv; prim = B.tri_id[leaf];
+            }
+        } else if (O.kind == OBJ_SPHERE) {  // objects.h:45-68
+            d3 l = mk(O.a[0], O.a[1], O.a[2]) - o;
+            double tca = dot(l, d);
+            double l2 = dot(l, l);
+            if (!(tca < 0 && l2 > O.r2)) {
+                double d2 = dot(l, l) - tca * tca;
+                if (!(d2 > O.r2)) {
+                    double thc = sqrt(O.r2 - d2);
+                    double t0 = tca - thc, t1 = tca + thc;
+                    double len = (t0 < 0) ? t1 : t0;
+                    if (len < nearest) {
+                        d3 p = o + d * len;
+                        id = i; nearest = len; prim = -1;
+                        nrm = normalize(p - mk(O.a[0], O.a[1], O.a[2]));
+                    }
+                }
+            }
+        } else {  // OBJ_BEZIER
+            double len; d3 nv;
+            if (bezier_intersect(S.bez[O.aux], o, d, len, nv)) {
+                if (len < nearest) { id = i; nearest = len; nrm = nv; prim = -1; }
+            }
+        }
+    }
+    h.obj = id;
+    h.t = nearest;
+    h.n = nrm;
+    h.prim = prim;
+    return id >= 0;
+}
+
+// Texture::color, texture.h:39-72; Plane::getSurfaceColor objects.h:533-539
+__device__ __forceinline__ d3 surface_color(const SceneDev &S, int obj, d3 point) {
+    const ObjDev &O = S.obj[obj];
+    d3 flat = mk(O.col[0], O.col[1], O.col[2]);
+    if (O.kind != OBJ_PLANE || O.tex < 0) return flat;
+    const TexDev &T = S.tex[O.tex];
+    const double texteps = 1e-2;
+    d3 n = mk(T.n[0], T.n[1], T.n[2]);
+    d3 dd = point - mk(T.p[0], T.p[1], T.p[2]);
+    dd = dd - n * dot(dd, n);
+    int r, c;
+    if (dd.x < texteps && dd.x > -texteps) {
+        if (0 < dd.y && dd.y < T.lenx && 0 < dd.z && dd.z < T.leny) {
+            r = (int)floor(dd.y / T.lenx * T.H);
+            c = (int)floor(dd.z / T.leny * T.W);
+        } else return flat;
+    } else if (dd.y < texteps && dd.y > -texteps) {
+        if (0 < dd.x && dd.x < T.lenx && 0 < dd.z && dd.z < T.leny) {
+            c = (int)floor(dd.x / T.lenx * T.W);
+            r = (int)floor(dd.z / T.leny * T.H);
+        } else return flat;
+    } else if (dd.z < texteps && dd.z > -texteps) {
+        if (0 < dd.x && dd.x < T.lenx && 0 < dd.y && dd.y < T.leny) {
+            c = (int)floor(dd.x / T.lenx * T.W);
+            r = T.H - 1 - (int)floor(dd.y / T.leny * T.H);
+        } else return flat;
+    } else {
+        return flat;
+    }
+    r = r < 0 ? 0 : (r >= T.H ? T.H - 1 : r);
+    c = c < 0 ? 0 : (c >= T.W ? T.W - 1 : c);
+    uchar4 tx = __ldg(T.texels + (size_t)r * T.W + c);
+    return mk((double)tx.x / 256.0, (double)tx.y / 256.0, (double)tx.z / 256.0);
+}
+
+// hash.h:35-42
+__host__ __device__ __forceinline__ void cell_coord(d3 p, double celllength, int &ix, int &iy, int &iz) {
+    ix = (int)floor((p.x - (-35.0)) / celllength);
+    iy = (int)floor((p.y - (-35.0)) / celllength);
+    iz = (int)floor((p.z - (-15.0)) / celllength);
+}
+__host__ __device__ __forceinline__ uint32_t cell_hash(int ix, int iy, int iz, uint32_t hashsize) {
+    return (((uint32_t)ix * 73856093u) ^ ((uint32_t)iy * 19349663u) ^ ((uint32_t)iz * 83492791u)) % hashsize;
+}
+
+}  // namespace cgrt

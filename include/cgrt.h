@@ -1,0 +1,148 @@
+/* cgrt.h — C ABI of the B200-native progressive-photon-mapping hot path (libcgrt.so).
+ *
+ * This is the drop-in boundary for CGRayTracing's trace()/render() path: the reference's host classes
+ * (Object/Sphere/Plane/TriangleMesh/Bezier/Texture/Hashtable, headers/objects.h, bezier.h, texture.h, hash.h) stay on
+ * the host as thin descriptors (cgraytracing_b200/host/cgrt_host.hpp); everything they compute on the hot path is
+ * done behind these entry points by hand-written sm_100a kernels. Plain pointers and sizes only; no C++/torch types.
+ *
+ * Conventions: every function returns 0 on success or a negative cgrt_status; never throws; no global state; one
+ * opaque cgrt_ctx per GPU; calls on one ctx are not thread-safe; the caller owns every host buffer; the ctx owns all
+ * device memory. All `double*`/`int*` arguments are HOST pointers unless the name ends in `_dev`.
+ * Citations are file:line in the reference (haoyuzhao123/CGRayTracing).
+ */
+#ifndef CGRT_H_
+#define CGRT_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct cgrt_ctx cgrt_ctx;
+
+typedef enum cgrt_status {
+    CGRT_OK = 0,
+    CGRT_ERR_INVALID = -1,   /* bad argument / call order */
+    CGRT_ERR_CUDA = -2,      /* a CUDA call failed; see cgrt_last_error */
+    CGRT_ERR_NO_DEVICE = -3, /* no usable GPU: there is NO CPU fallback */
+    CGRT_ERR_CAPACITY = -4,  /* a fixed-size table (objects, textures, BVHs, queue) is full */
+    CGRT_ERR_NCCL = -5
+} cgrt_status;
+
+/* Every compile-time constant of render()/trace() (main.cpp:28-36, 177-184, 222-224) as a field. */
+typedef struct cgrt_config {
+    int32_t width, height;      /* main.cpp:28-29 */
+    int32_t max_depth;          /* MAX_DEPTH, main.cpp:35 */
+    int32_t num_of_samples;     /* main.cpp:177 */
+    int32_t use_dof;            /* 1: trace the thin-lens ray of main.cpp:203-207 instead of the pinhole ray of :209 */
+    int32_t hashsize;           /* Hashtable(hashsize, r), main.cpp:184 */
+    int32_t accum_mode;         /* 0: fp64 atomics (parity), 1: one red.global.add.v4.f32 per deposit (fast) */
+    int32_t reserved;
+    double alpha;               /* main.cpp:36 */
+    double focus_plane;         /* main.cpp:178 */
+    double lens_radius;         /* main.cpp:179 */
+    double lightorg[3];         /* main.cpp:180 */
+    double camorg[3];           /* main.cpp:181 */
+    uint64_t seed;              /* Philox key (replaces srand(time), main.cpp:229,269) */
+} cgrt_config;
+
+typedef struct cgrt_counters {
+    uint64_t eye_segments, photon_segments; /* trace() calls that reached the closest-hit loop, main.cpp:50 */
+    uint64_t diffuse_hits;                  /* photon hits on diffuse surfaces, main.cpp:101 */
+    uint64_t candidates, deposits;          /* hitpoints scanned / accepted in the 27-cell gather, main.cpp:114-116 */
+    uint64_t node_visits, tri_tests;        /* only filled by cgrt_count_traversal (a counting build of the same traversal) */
+    uint64_t hitpoints;                     /* "hitpoints: %d", main.cpp:265 */
+    uint64_t gpu_launches;                  /* kernels launched by this ctx so far */
+} cgrt_counters;
+
+/* ---- lifecycle ------------------------------------------------------------------------------------------------ */
+int cgrt_create(int device, cgrt_ctx **out);
+int cgrt_destroy(cgrt_ctx *ctx);
+const char *cgrt_last_error(const cgrt_ctx *ctx); /* never NULL */
+int cgrt_version(void);
+void cgrt_default_config(cgrt_config *cfg);       /* the reference's literals */
+int cgrt_set_config(cgrt_ctx *ctx, const cgrt_config *cfg);
+/* The CUDA stream (cudaStream_t as void*) all kernels of this ctx are launched on; time with events on THIS stream. */
+int cgrt_get_stream(cgrt_ctx *ctx, void **stream);
+int cgrt_synchronize(cgrt_ctx *ctx);
+
+/* ---- scene: same argument meaning as the reference constructors; object ids are insertion order (main.cpp:355-378) */
+/* Texture(data,n,p,lx,ly,flag) texture.h:19 with data[i][j] = rgb8/256 (main.cpp:303-316). rgb is h*w*3 bytes. */
+int cgrt_add_texture(cgrt_ctx *ctx, const uint8_t *rgb, int w, int h, const double n[3], const double p[3], double lenx,
+                     double leny, int isbump, int *tex_id);
+/* Sphere(c,r,sc,refl,transp) objects.h:28-38 */
+int cgrt_add_sphere(cgrt_ctx *ctx, const double c[3], double r, const double col[3], double refl, double transp, int *obj_id);
+/* Plane(p,n,sc,refl,transp,tx) objects.h:480; tex_id < 0: untextured. A bump texture on an n=(0,1,0) plane builds the
+ * displaced height-field mesh of objects.h:482-503 on the device. */
+int cgrt_add_plane(cgrt_ctx *ctx, const double p[3], const double n[3], const double col[3], double refl, double transp,
+                   int tex_id, int *obj_id);
+/* TriangleMesh(...) objects.h:338-403 after loading: tri9 = ntri x (pa,pb,pc) world-space fp64; objtype = typeofdata. */
+int cgrt_add_mesh(cgrt_ctx *ctx, const double *tri9, int ntri, const double col[3], double refl, double transp, int objtype,
+                  int *obj_id);
+/* Bezier(points,pos,sc,refl,transp) bezier.h:44-45; ncp <= 7. */
+int cgrt_add_bezier(cgrt_ctx *ctx, const double *cp3, int ncp, const double pos[3], const double col[3], double refl,
+                    double transp, int *obj_id);
+/* Uploads, builds every LBVH (Morton codes -> radix sort -> Karras hierarchy -> refit) and freezes the scene. */
+int cgrt_commit_scene(cgrt_ctx *ctx);
+
+/* ---- parity hooks ---------------------------------------------------------------------------------------------- */
+/* Closest hit of main.cpp:50-76 for n rays: t, face-forwarded normal, object id (-1 miss), into flag, primitive id
+ * (original triangle index for meshes / height-fields, else -1). Any output may be NULL. */
+int cgrt_intersect_batch(cgrt_ctx *ctx, int64_t n, const double *org, const double *dir, double *t, double *nrm,
+                         double *nrm_raw, int32_t *obj, int32_t *into, int32_t *prim);
+/* Hashtable ctor + compute_coord + hash (hash.h:22-42) for n positions: key[n], ixyz[3n] (either may be NULL). */
+int cgrt_hash_keys(cgrt_ctx *ctx, int64_t n, const double *pos, int hashsize, double celllength_in, uint32_t *key,
+                   int32_t *ixyz);
+/* getSurfaceColor (objects.h:533-539 / texture.h:39-72) of object obj at n points. */
+int cgrt_surface_color(cgrt_ctx *ctx, int obj, int64_t n, const double *pos, double *col);
+/* Triangles of object obj's BVH in original order (mesh: as given; bump plane: objects.h:485-499). tri9 NULL: count only. */
+int cgrt_object_triangles(cgrt_ctx *ctx, int obj, double *tri9, int64_t cap, int64_t *ntri);
+/* The Philox sampling definitions: what = 0 sphere, 1 hemisphere about aux, 2 lens disc radius aux[0], 3 three U(0,1). */
+int cgrt_sample(cgrt_ctx *ctx, uint64_t seed, uint32_t pass, uint64_t path, uint32_t dim, int what, const double aux[3],
+                double out[3]);
+/* Hand-written LSD radix sort (the one used for Morton codes and hitpoint keys): sorts key[n] (bits [0,nbits)) stably and
+ * returns the permutation. */
+int cgrt_radix_sort(cgrt_ctx *ctx, int64_t n, const uint64_t *key_in, int nbits, uint64_t *key_out, uint32_t *perm);
+/* Counting build of the traversal kernel over n rays: fills counters.node_visits / tri_tests (roofline accounting). */
+int cgrt_count_traversal(cgrt_ctx *ctx, int64_t n, const double *org, const double *dir, uint64_t *node_visits,
+                         uint64_t *tri_tests);
+
+/* ---- passes ---------------------------------------------------------------------------------------------------- */
+/* Eye pass (main.cpp:183-219) over image rows [y0,y1) as an iterative wavefront; appends hitpoints. */
+int cgrt_eye_pass(cgrt_ctx *ctx, int y0, int y1);
+/* Tile-sharded eye pass: export this rank's unsorted hitpoint records / import the union (all-gather in between).
+ * Records are CGRT_HP_RECORD_DOUBLES doubles each. */
+#define CGRT_HP_RECORD_DOUBLES 12
+int cgrt_export_hitpoints_dev(cgrt_ctx *ctx, void **records_dev, int64_t *count);
+int cgrt_import_hitpoints_dev(cgrt_ctx *ctx, const void *records_dev, int64_t count);
+/* hash.h:43-54 + main.cpp:98 as a sort-based grid: keys -> radix sort on (key, creation order) -> cell-start table. */
+int cgrt_build_grid(cgrt_ctx *ctx);
+/* Photons with global indices [first, first+count) (main.cpp:231-247): emit, bounce, deposit into the per-round
+ * accumulators. Index k always draws the same Philox stream, whichever GPU traces it. */
+int cgrt_photon_pass(cgrt_ctx *ctx, uint64_t first, uint64_t count);
+/* Device view of the per-round accumulators {dflux[3], m} (4 x fp64 per hitpoint, canonical order) for the all-reduce. */
+int cgrt_accum_dev(cgrt_ctx *ctx, void **ptr_dev, int64_t *n_doubles);
+/* All-reduce the accumulators over an NCCL communicator (ncclComm_t as void*; NULL: single GPU, no-op). */
+int cgrt_allreduce_accum(cgrt_ctx *ctx, void *nccl_comm);
+/* Per-round radius/flux update (main.cpp:119-122 in its batched form, SURVEY Q1 "U2"), then clears the accumulators. */
+int cgrt_round_update(cgrt_ctx *ctx);
+/* main.cpp:252-258 (+ :403-411 when rgb8 != NULL: tone map, gamma, vertical flip). rgb: H*W*3 fp64, row h = image[h]. */
+int cgrt_gather_image(cgrt_ctx *ctx, double n_emitted, double *rgb, uint8_t *rgb8);
+
+/* ---- downloads (canonical order: bucket ascending, creation order inside a bucket; main.cpp:252-254) ------------- */
+int cgrt_num_hitpoints(cgrt_ctx *ctx, int64_t *n);
+int cgrt_download_hitpoints(cgrt_ctx *ctx, double *pos, double *normal, double *f, double *flux, double *r2, int32_t *n,
+                            int32_t *hw, uint32_t *key, uint32_t *seq);
+int cgrt_download_accum(cgrt_ctx *ctx, double *dflux, double *m);
+int cgrt_download_grid(cgrt_ctx *ctx, uint32_t *cell_start /* hashsize+1 */);
+int cgrt_get_counters(cgrt_ctx *ctx, cgrt_counters *out);
+/* Timing of the last pass on the ctx stream (CUDA events), milliseconds: [0] eye, [1] grid, [2] photon trace kernels,
+ * [3] photon deposit kernels, [4] update, [5] gather. */
+int cgrt_get_timings(cgrt_ctx *ctx, double ms[8]);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* CGRT_H_ */

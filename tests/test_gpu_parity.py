@@ -1,0 +1,217 @@
+"""GPU parity tests proper: the CUDA path (through the C ABI) against the CPU oracle on the same seeded inputs.
+Bars: cell keys / sorted order bit-exact; t and normals <= 1e-5 relative (we assert bit-exact,
+the stronger statement, where the arithmetic is the same); accepted-photon counts equal; flux within 1e-9 (fp64 atomic order)."""
+import numpy as np
+import pytest
+
+from tests.util import camera_rays, random_rays, rel_err
+
+pytestmark = pytest.mark.gpu
+
+T_TOL = 1e-5  # relative, north_star
+
+
+def make(gpu, ob, name, cfg_kw=None, max_tris=None):
+    cfg = gpu.RenderConfig(**(cfg_kw or {}))
+    s = gpu.preset(name, max_tris=max_tris)
+    return s, cfg, gpu.Context(0, s, cfg), ob.Oracle(s, cfg)
+
+
+def test_hash_keys_bit_exact(gpu, oracle_lib):
+    ob = oracle_lib
+    rng = np.random.default_rng(3)
+    pos = rng.uniform(-40, 60, (200000, 3))
+    pos[:1000] = np.round(pos[:1000] * 4) / 4  # cell-boundary-ish values
+    with gpu.Context(0) as g:
+        for h in (512, 768, 1024, 1080, 4096):
+            k, ixyz = g.hash_keys(pos, 1000001, 200.0 / h)
+            ok, oixyz = ob.hash_keys(pos, 1000001, 200.0 / h)
+            assert np.array_equal(ixyz, oixyz)
+            assert np.array_equal(k, ok)
+        k, _ = g.hash_keys(pos, 16777259, 200.0 / 4096)
+        ok, _ = ob.hash_keys(pos, 16777259, 200.0 / 4096)
+        assert np.array_equal(k, ok)
+
+
+def test_radix_sort_stable(gpu):
+    rng = np.random.default_rng(4)
+    with gpu.Context(0) as g:
+        for n, bits in ((1, 8), (255, 16), (4096, 24), (100003, 40), (1 << 20, 52)):
+            keys = rng.integers(0, 1 << bits, n, dtype=np.uint64)
+            keys[: n // 3] = keys[0]  # many duplicates: stability matters
+            out, perm = g.radix_sort(keys, bits)
+            ref = np.argsort(keys, kind="stable")
+            assert np.array_equal(perm, ref.astype(np.uint32))
+            assert np.array_equal(out, keys[ref])
+
+
+def test_philox_sampling_matches_oracle(gpu, oracle_lib):
+    ob = oracle_lib
+    with gpu.Context(0) as g:
+        for path in (0, 1, 12345678901, 2**40 + 17):
+            for what, aux in ((0, (0, 0, 0)), (1, (0.3, -0.8, 0.52)), (2, (1.5, 0, 0)), (3, (0, 0, 0))):
+                a = g.sample(20261018, 1, path, 3, what, aux)
+                b = ob.sample(20261018, 1, path, 3, what, aux)
+                assert np.array_equal(a, b), (path, what)
+
+
+@pytest.mark.parametrize("name,max_tris", [("c1_spheres", None), ("c2_bunny_chess", None), ("c3_dragon_glass", 20000), ("c4_bump_dof", None),
+                                           ("default_bump", 20000)])
+def test_intersect_batch_matches_oracle(gpu, oracle_lib, name, max_tris):
+    s, cfg, g, o = make(gpu, oracle_lib, name, dict(into_rule=1), max_tris)
+    with g:
+        for org, dr in (random_rays(40000, 5), camera_rays(1024, 768, 7)):
+            a = g.intersect_batch(org, dr)
+            b = o.intersect_batch(org, dr)
+            assert np.array_equal(a["obj"], b["obj"])
+            hit = b["obj"] >= 0
+            assert hit.mean() > 0.9
+            # north-star bar
+            assert rel_err(a["t"][hit], b["t"][hit]).max() <= T_TOL
+            assert np.abs(a["nrm"][hit] - b["nrm"][hit]).max() <= T_TOL
+            # what we actually achieve: the same fp64 arithmetic -> identical bits (ties between coplanar triangles aside)
+            same_prim = a["prim"] == b["prim"]
+            assert same_prim.mean() > 0.999
+            assert np.array_equal(a["t"][same_prim], b["t"][same_prim])
+            assert np.array_equal(a["nrm"][same_prim], b["nrm"][same_prim])
+            assert np.array_equal(a["into"][same_prim], b["into"][same_prim])
+
+
+def test_bvh_equals_brute_force(gpu, oracle_lib):
+    """Property: LBVH closest hit == brute force over all triangles."""
+    s, cfg, g, o = make(gpu, oracle_lib, "c3_dragon_glass", dict(into_rule=1), 30000)
+    mesh_id = len(s.objects) - 1
+    with g:
+        org, dr = random_rays(3000, 9)
+        a = g.intersect_batch(org, dr)
+        hit, ln, tri = o.mesh_brute(mesh_id, org, dr)
+        on_mesh = a["obj"] == mesh_id
+        # every GPU mesh hit is the brute-force closest triangle
+        assert np.array_equal(a["t"][on_mesh], ln[on_mesh])
+        # and where brute force hits the mesh closer than anything else the GPU reports the mesh
+        walls = o.intersect_batch(org, dr)
+        assert np.array_equal(on_mesh, walls["obj"] == mesh_id)
+
+
+def test_bump_heightfield_triangles_bit_exact(gpu, oracle_lib):
+    s, cfg, g, o = make(gpu, oracle_lib, "c4_bump_dof")
+    with g:
+        t = g.object_triangles(0)
+        assert len(t) == 146744
+        assert np.array_equal(t, o.bump_triangles(0))
+
+
+def test_surface_color_matches_oracle(gpu, oracle_lib):
+    s, cfg, g, o = make(gpu, oracle_lib, "c2_bunny_chess")
+    rng = np.random.default_rng(6)
+    pos = np.stack([rng.uniform(-25, 25, 50000), np.full(50000, -20.0), rng.uniform(-5, 45, 50000)], -1)
+    with g:
+        assert np.array_equal(g.surface_color(0, pos), o.surface_color(0, pos))
+        assert np.array_equal(g.surface_color(1, pos), o.surface_color(1, pos))
+
+
+@pytest.mark.parametrize("name,max_tris,W,H", [("c1_spheres", None, 256, 192), ("c2_bunny_chess", None, 256, 256), ("c3_dragon_glass", 30000, 192, 192),
+                                               ("default_bump", 20000, 128, 96)])
+def test_eye_pass_hitpoints_bit_exact(gpu, oracle_lib, name, max_tris, W, H):
+    """Hitpoints, their cell keys and their sorted (canonical) order equal the oracle's bit for bit."""
+    s, cfg, g, o = make(gpu, oracle_lib, name, dict(width=W, height=H, into_rule=1, update_mode=1), max_tris)
+    with g:
+        g.eye_pass()
+        g.build_grid()
+        a = g.download_hitpoints()
+        o.eye_pass()
+        b = o.download_hitpoints()
+        assert len(a["pos"]) == len(b["pos"]) > 0
+        assert np.array_equal(a["key"], b["key"])
+        assert np.array_equal(a["hw"], b["hw"])
+        for k in ("pos", "normal", "f", "r2"):
+            assert np.array_equal(a[k], b[k]), k
+        # creation sequence (path*16+dfs code) orders exactly like the oracle's insertion counter inside every bucket
+        assert np.array_equal(a["seq"], (b["path"] * 16 + b["code"]).astype(np.uint32))
+        cs = g.download_grid()
+        assert cs[0] == 0 and cs[-1] == len(a["key"])
+        counts = np.bincount(b["key"], minlength=cfg.hashsize)
+        assert np.array_equal(np.diff(cs.astype(np.int64)), counts)
+        assert g.counters()["eye_segments"] == o.counters()["eye_segments"]
+
+
+@pytest.mark.parametrize("name,max_tris", [("c1_spheres", None), ("c2_bunny_chess", None), ("c3_dragon_glass", 30000), ("default_bump", 20000)])
+def test_photon_rounds_match_oracle(gpu, oracle_lib, name, max_tris):
+    """Two U2 rounds with the same Philox streams: integer counts equal, flux equal to fp64-atomic-order rounding, image equal."""
+    W, H, NPH = 160, 120, 30000
+    s, cfg, g, o = make(gpu, oracle_lib, name, dict(width=W, height=H, into_rule=1, update_mode=1), max_tris)
+    with g:
+        g.eye_pass(); g.build_grid()
+        o.eye_pass()
+        for rnd in range(2):
+            g.photon_pass(rnd * NPH, NPH)
+            o.photon_pass(rnd * NPH, NPH)
+            df, m = g.download_accum()
+            odf, om = o.download_accum()
+            assert np.array_equal(m.astype(np.int64), om.astype(np.int64))
+            assert np.allclose(df, odf, rtol=1e-9, atol=1e-12)
+            g.round_update(); o.round_update()
+        a = g.download_hitpoints(); b = o.download_hitpoints()
+        assert np.array_equal(a["n"], b["n"])
+        assert np.array_equal(a["r2"], b["r2"])
+        assert np.allclose(a["flux"], b["flux"], rtol=1e-9, atol=1e-12)
+        img = g.gather_image(2.0 * NPH)
+        assert np.allclose(img, o.gather_image(2.0 * NPH), rtol=1e-9, atol=1e-12)
+        gc, oc = g.counters(), o.counters()
+        for k in ("photon_segments", "diffuse_hits", "candidates", "deposits"):
+            assert gc[k] == oc[k], k
+
+
+def test_photon_shards_are_invariant(gpu, oracle_lib):
+    """Photons [0,N) in one call == two disjoint sub-ranges (what two GPUs would trace) summed: same counts, same flux."""
+    s = gpu.preset("c2_bunny_chess")
+    cfg = gpu.RenderConfig(width=128, height=96)
+    N = 20000
+    with gpu.Context(0, s, cfg) as g1, gpu.Context(0, s, cfg) as g2:
+        for g in (g1, g2):
+            g.eye_pass(); g.build_grid()
+        g1.photon_pass(0, N)
+        g2.photon_pass(N // 2, N - N // 2)
+        g2.photon_pass(0, N // 2)
+        d1, m1 = g1.download_accum(); d2, m2 = g2.download_accum()
+        assert np.array_equal(m1, m2)
+        assert np.allclose(d1, d2, rtol=1e-9, atol=1e-12)
+
+
+def test_f32_accumulators_close_to_f64(gpu):
+    s = gpu.preset("c2_bunny_chess")
+    cfg = gpu.RenderConfig(width=128, height=96)
+    with gpu.Context(0) as g64, gpu.Context(0) as g32:
+        for g, mode in ((g64, 0), (g32, 1)):
+            g.set_config(cfg, accum_mode=mode)
+            s.build_into(g); g.commit()
+            g.eye_pass(); g.build_grid(); g.photon_pass(0, 30000)
+        d64, m64 = g64.download_accum(); d32, m32 = g32.download_accum()
+        assert np.array_equal(m64, m32)
+        assert np.allclose(d32, d64, rtol=1e-4, atol=1e-3)
+
+
+def test_tile_sharded_eye_pass_equals_unsharded(gpu):
+    s = gpu.preset("c2_bunny_chess")
+    cfg = gpu.RenderConfig(width=128, height=96)
+    with gpu.Context(0, s, cfg) as g1, gpu.Context(0, s, cfg) as g2:
+        g1.eye_pass(); g1.build_grid()
+        g2.eye_pass(48, 96); g2.eye_pass(0, 48); g2.build_grid()
+        a, b = g1.download_hitpoints(), g2.download_hitpoints()
+        for k in a:
+            assert np.array_equal(a[k], b[k]), k
+
+
+def test_empty_and_error_paths(gpu):
+    with gpu.Context(0) as g:
+        g.set_config(gpu.RenderConfig(width=16, height=16))
+        with pytest.raises(gpu.CgrtError):
+            g.eye_pass()  # scene not committed
+        g.commit()  # an empty scene is legal: every ray misses
+        g.eye_pass(); g.build_grid()
+        assert g.num_hitpoints() == 0
+        g.photon_pass(0, 100)
+        g.round_update()
+        assert np.all(g.gather_image(100.0) == 0)
+        with pytest.raises(gpu.CgrtError):
+            g.commit()
