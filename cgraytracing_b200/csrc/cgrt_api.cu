@@ -74,6 +74,7 @@ struct cgrt_ctx {
     double ms[8] = {0, 0, 0, 0, 0, 0, 0, 0};
     cudaEvent_t ev[2] = {nullptr, nullptr};
     size_t photon_chunk = 4u << 20;
+    int counting = 0;  // 1: photon trace kernels also count BVH node visits / triangle tests (roofline accounting)
 };
 
 namespace {
@@ -816,12 +817,12 @@ int cgrt_photon_pass(cgrt_ctx *ctx, uint64_t first, uint64_t count) {
             CK(cudaMemsetAsync(ctx->d_qcount + (cur ^ 1), 0, sizeof(unsigned int), ctx->stream));
             CK(cudaMemsetAsync(ctx->d_qcount + 2, 0, sizeof(unsigned int), ctx->stream));
             CK(cudaEventRecord(e0, ctx->stream));
-            if (depth == 0)
-                photon_trace_kernel<true><<<nblk(n, 128), 128, 0, ctx->stream>>>(ctx->S, P, depth, ctx->q[cur], (unsigned int)n, base, ctx->q[cur ^ 1],
-                                                                                 ctx->d_qcount + (cur ^ 1), ctx->dq, ctx->d_qcount + 2, ctx->d_ctr);
-            else
-                photon_trace_kernel<false><<<nblk(n, 128), 128, 0, ctx->stream>>>(ctx->S, P, depth, ctx->q[cur], (unsigned int)n, base, ctx->q[cur ^ 1],
-                                                                                  ctx->d_qcount + (cur ^ 1), ctx->dq, ctx->d_qcount + 2, ctx->d_ctr);
+#define LAUNCH_PT(F, C)                                                                                                                  \
+    photon_trace_kernel<F, C><<<nblk(n, 128), 128, 0, ctx->stream>>>(ctx->S, P, depth, ctx->q[cur], (unsigned int)n, base, ctx->q[cur ^ 1], \
+                                                                     ctx->d_qcount + (cur ^ 1), ctx->dq, ctx->d_qcount + 2, ctx->d_ctr, ctx->d_tc)
+            if (ctx->counting) { if (depth == 0) LAUNCH_PT(true, true); else LAUNCH_PT(false, true); }
+            else { if (depth == 0) LAUNCH_PT(true, false); else LAUNCH_PT(false, false); }
+#undef LAUNCH_PT
             ctx->launches++;
             CK(cudaEventRecord(e1, ctx->stream));
             unsigned int counts[2];
@@ -995,8 +996,21 @@ int cgrt_get_counters(cgrt_ctx *ctx, cgrt_counters *out) {
     out->diffuse_hits = ctx->diffuse_hits;
     out->candidates = c.candidates;
     out->deposits = c.deposits;
+    {
+        TravCounters tc;
+        CK(cudaMemcpy(&tc, ctx->d_tc, sizeof tc, cudaMemcpyDeviceToHost));
+        out->node_visits = tc.node_visits;
+        out->tri_tests = tc.tri_tests;
+    }
     out->hitpoints = ctx->grid_built ? ctx->nhp : ctx->hp_count;
     out->gpu_launches = ctx->launches;
+    return CGRT_OK;
+}
+
+int cgrt_set_counting(cgrt_ctx *ctx, int on) {
+    if (!ctx) return CGRT_ERR_INVALID;
+    ctx->counting = on != 0;
+    CK(cudaMemset(ctx->d_tc, 0, sizeof(TravCounters)));
     return CGRT_OK;
 }
 

@@ -230,10 +230,11 @@ __global__ void lower_bound_table_kernel(const uint32_t *__restrict__ keys32, co
 // =================================================================================================================
 // Photon pass: trace kernel (emission K10 fused into depth 0) + deposit kernel.
 // =================================================================================================================
-template <bool FIRST>
+template <bool FIRST, bool COUNT>
 __global__ void __launch_bounds__(128) photon_trace_kernel(const __grid_constant__ SceneDev S, const __grid_constant__ PassParams P, int depth,
                                                            RayQueue qin, unsigned int n_in, uint64_t first_index, RayQueue qout,
-                                                           unsigned int *n_out, DepositQueue dq, unsigned int *n_dq, Counters *ctr) {
+                                                           unsigned int *n_out, DepositQueue dq, unsigned int *n_dq, Counters *ctr,
+                                                           TravCounters *tcg) {
     unsigned int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n_in) return;
     d3 o, d, flux;
@@ -254,7 +255,13 @@ __global__ void __launch_bounds__(128) photon_trace_kernel(const __grid_constant
         off = qin.id[i];
     }
     Hit hit;
-    bool found = closest_hit<false>(S, o, d, hit, nullptr);
+    TravCounters tcl;
+    tcl.node_visits = 0; tcl.tri_tests = 0;
+    bool found = closest_hit<COUNT>(S, o, d, hit, &tcl);
+    if (COUNT) {
+        atomicAdd(&tcg->node_visits, tcl.node_visits);
+        atomicAdd(&tcg->tri_tests, tcl.tri_tests);
+    }
     {
         unsigned int act = __activemask();
         if ((threadIdx.x & 31) == (__ffs(act) - 1)) atomicAdd(&ctr->photon_segments, (unsigned long long)__popc(act));

@@ -138,7 +138,10 @@ int cgrt_download_hitpoints(cgrt_ctx *ctx, double *pos, double *normal, double *
 int cgrt_download_accum(cgrt_ctx *ctx, double *dflux, double *m);
 int cgrt_download_grid(cgrt_ctx *ctx, uint32_t *cell_start /* hashsize+1 */);
 int cgrt_get_counters(cgrt_ctx *ctx, cgrt_counters *out);
-/* Timing of the last pass on the ctx stream (CUDA events), milliseconds: [0] eye, [1] grid, [2] photon trace kernels,
+/* on != 0: the photon trace kernels run their counting build (same traversal + node-visit / triangle-test counters,
+ * reported by cgrt_get_counters). Used outside timed regions to derive the algorithmic bytes of the roofline. */
+int cgrt_set_counting(cgrt_ctx *ctx, int on);
+/* Accumulated device time per phase on the ctx stream (CUDA events), milliseconds: [0] eye, [1] grid, [2] photon trace kernels,
  * [3] photon deposit kernels, [4] update, [5] gather. */
 int cgrt_get_timings(cgrt_ctx *ctx, double ms[8]);
 
