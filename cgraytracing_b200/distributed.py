@@ -1,0 +1,150 @@
+"""render() over the GPUs of one box: one process per GPU, torch.distributed for the plumbing (NCCL over NVLink/NVSwitch).
+
+The reference's render() (main.cpp:169-266) runs its photon loop on 8 OpenMP threads over ONE shared hash table
+(main.cpp:225-249). Here the same partitioning is made explicit and replayable:
+
+  eye pass     image rows are split into contiguous tiles, one per rank (main.cpp:185-187 is a plain double loop);
+               the per-rank hitpoint records are all-gathered and every rank builds the SAME sorted grid from the union
+               (the sort key carries the creation sequence, so the canonical order does not depend on who traced what);
+  photon pass  rank g traces the global photon indices [first + g*P/G, first + (g+1)*P/G) of the round — photon k draws the
+               same Philox stream whichever GPU traces it — against the replicated hitpoint set. No data-path collective;
+  round update one all-reduce(sum) of the per-hitpoint accumulators {dflux.xyz, m}, then every rank applies the same
+               radius/flux update (main.cpp:119-122 in its per-round form) and stays bit-identical to its peers.
+
+`ShardedRenderer` is written against a small engine protocol so that the host logic (ranges, collective order) can be
+exercised on CPU with the gloo backend; the product engine is `GpuEngine` (a `Context` behind the C ABI).
+"""
+from __future__ import annotations
+
+from typing import Tuple
+
+import numpy as np
+
+HP_RECORD_DOUBLES = 12  # CGRT_HP_RECORD_DOUBLES, include/cgrt.h
+
+
+def split_range(first: int, count: int, rank: int, world: int) -> Tuple[int, int]:
+    """Contiguous, disjoint, covering split of [first, first+count) into `world` parts; the remainder goes to the low ranks."""
+    if world <= 0 or not (0 <= rank < world) or count < 0:
+        raise ValueError("bad shard request")
+    base, rem = divmod(count, world)
+    lo = first + rank * base + min(rank, rem)
+    return lo, base + (1 if rank < rem else 0)
+
+
+def photon_shard(round_index: int, photons_per_round: int, rank: int, world: int) -> Tuple[int, int]:
+    """Global photon index range of `rank` in round `round_index` (round r owns [r*P, (r+1)*P))."""
+    return split_range(round_index * photons_per_round, photons_per_round, rank, world)
+
+
+def row_shard(height: int, rank: int, world: int) -> Tuple[int, int]:
+    """Image rows [y0, y1) of `rank` for the tile-sharded eye pass."""
+    y0, n = split_range(0, height, rank, world)
+    return y0, y0 + n
+
+
+class _DevArray:
+    def __init__(self, ptr, n, typestr):
+        self.__cuda_array_interface__ = {"shape": (n,), "typestr": typestr, "data": (ptr, False), "version": 2}
+
+
+class GpuEngine:
+    """Adapter of a `Context` (C ABI) to the engine protocol; tensors are zero-copy views of ctx-owned device memory."""
+
+    def __init__(self, ctx, device: int):
+        import torch
+
+        self.ctx, self.device, self.torch = ctx, device, torch
+
+    def eye_pass(self, y0, y1):
+        self.ctx.eye_pass(y0, y1)
+
+    def export_hitpoints(self):
+        ptr, n = self.ctx.export_hitpoints_dev()
+        if n == 0:
+            return self.torch.zeros((0, HP_RECORD_DOUBLES), dtype=self.torch.float64, device=f"cuda:{self.device}")
+        return self.torch.as_tensor(_DevArray(ptr, n * HP_RECORD_DOUBLES, "<f8"), device=f"cuda:{self.device}").view(n, HP_RECORD_DOUBLES)
+
+    def import_hitpoints(self, rec):
+        rec = rec.contiguous()
+        self.torch.cuda.current_stream().synchronize()
+        self.ctx.import_hitpoints_dev(rec.data_ptr(), rec.shape[0])
+
+    def build_grid(self):
+        self.ctx.build_grid()
+        ptr, n = self.ctx.accum_dev()
+        ts = "<f8" if self.ctx.accum_mode == 0 else "<f4"
+        self._acc = self.torch.as_tensor(_DevArray(ptr, n, ts), device=f"cuda:{self.device}") if n else None
+
+    def photon_pass(self, first, count):
+        self.ctx.photon_pass(first, count)
+
+    def accum_tensor(self):
+        """The live accumulator buffer: reduced in place."""
+        self.ctx.synchronize()
+        return self._acc
+
+    def accum_commit(self, t):
+        self.torch.cuda.current_stream().synchronize()
+
+    def round_update(self):
+        self.ctx.round_update()
+
+    def gather_image(self, n_emitted):
+        return self.ctx.gather_image(n_emitted)
+
+
+class ShardedRenderer:
+    def __init__(self, engine, rank: int = 0, world: int = 1, group=None, shard_eye: bool = True):
+        self.e, self.rank, self.world, self.group, self.shard_eye = engine, rank, world, group, shard_eye
+        self.rounds_done = 0
+        self.emitted = 0
+
+    # -- eye pass + grid
+    def eye(self, height: int):
+        if self.world == 1 or not self.shard_eye:
+            self.e.eye_pass(0, height)
+        else:
+            import torch
+            import torch.distributed as dist
+
+            y0, y1 = row_shard(height, self.rank, self.world)
+            if y1 > y0:
+                self.e.eye_pass(y0, y1)
+            mine = self.e.export_hitpoints()
+            counts = torch.zeros(self.world, dtype=torch.int64, device=mine.device)
+            counts[self.rank] = mine.shape[0]
+            dist.all_reduce(counts, group=self.group)
+            counts = [int(c) for c in counts.tolist()]
+            cap = max(counts)
+            # equal-size all_gather (one NCCL call); ranks pad to the largest tile
+            padded = torch.zeros((cap, HP_RECORD_DOUBLES), dtype=torch.float64, device=mine.device)
+            padded[: mine.shape[0]] = mine
+            parts = [torch.empty_like(padded) for _ in range(self.world)]
+            dist.all_gather(parts, padded, group=self.group)
+            union = torch.cat([p[:c] for p, c in zip(parts, counts)], 0)
+            self.e.import_hitpoints(union)
+        self.e.build_grid()
+
+    # -- one round
+    def round(self, photons_per_round: int):
+        first, count = photon_shard(self.rounds_done, photons_per_round, self.rank, self.world)
+        if count:
+            self.e.photon_pass(first, count)
+        if self.world > 1:
+            import torch.distributed as dist
+
+            acc = self.e.accum_tensor()
+            if acc is not None and acc.numel():
+                dist.all_reduce(acc, group=self.group)
+                self.e.accum_commit(acc)
+        self.e.round_update()
+        self.rounds_done += 1
+        self.emitted += photons_per_round
+
+    def render(self, height: int, rounds: int, photons_per_round: int) -> np.ndarray:
+        """The whole of render(): eye pass, `rounds` photon rounds, image gather (identical on every rank)."""
+        self.eye(height)
+        for _ in range(rounds):
+            self.round(photons_per_round)
+        return self.e.gather_image(float(self.emitted))

@@ -210,6 +210,24 @@ class Oracle:
         self.L.orc_download_accum(self.h, _p(df, c_dp), _p(m, c_ip))
         return df, m
 
+    def upload_accum(self, dflux, m):
+        df = _d(dflux).reshape(-1, 3); mm = np.ascontiguousarray(m, dtype=np.int32)
+        assert len(df) == len(mm) == self.num_hitpoints()
+        self.L.orc_upload_accum(self.h, _p(df, c_dp), _p(mm, c_ip))
+
+    def export_hitpoints(self):
+        """-> float64 [n, 12] records in the GPU path's exchange format (cgrt_export_hitpoints_dev)."""
+        self.L.orc_export_hitpoints.restype = C.c_int64
+        n = self.L.orc_export_hitpoints(self.h, None)
+        rec = np.zeros((n, 12))
+        if n:
+            self.L.orc_export_hitpoints(self.h, _p(rec, c_dp))
+        return rec
+
+    def import_hitpoints(self, rec):
+        rec = _d(rec).reshape(-1, 12)
+        self.L.orc_import_hitpoints(self.h, C.c_int64(len(rec)), _p(rec, c_dp))
+
     def photon_pass(self, first, count, nthreads=1):
         sec = C.c_double(0)
         r = self.L.orc_photon_pass(self.h, C.c_uint64(first), C.c_uint64(count), int(nthreads), C.byref(sec))

@@ -339,6 +339,61 @@ int orc_download_accum(void *c_, double *dflux, int32_t *m) {
     return 0;
 }
 
+// Test plumbing for the 2-rank (gloo) sharding tests: write back all-reduced accumulators, and move hitpoint sets
+// between oracle instances in the GPU path's record format (12 doubles: pos, normal, f, bits(key<<32 | path*16+code),
+// bits(h<<32 | w), 0 — cgrt_export_hitpoints_dev, include/cgrt.h).
+int orc_upload_accum(void *c_, const double *dflux, const int32_t *m) {
+    Ctx *c = (Ctx *)c_;
+    c->index();
+    for (size_t i = 0; i < c->canon.size(); i++) {
+        Hitpoint *hp = const_cast<Hitpoint *>(c->canon[i]);
+        if (dflux) hp->dflux = v3(dflux + 3 * i);
+        if (m) hp->m = m[i];
+    }
+    return 0;
+}
+int64_t orc_export_hitpoints(void *c_, double *rec12) {
+    Ctx *c = (Ctx *)c_;
+    c->index();
+    for (size_t i = 0; rec12 && i < c->canon.size(); i++) {
+        const Hitpoint &hp = *c->canon[i];
+        double *r = rec12 + 12 * i;
+        st3(r, hp.pos); st3(r + 3, hp.normal); st3(r + 6, hp.f);
+        int ix, iy, iz;
+        c->R.htable->compute_coord(hp.pos.x, hp.pos.y, hp.pos.z, ix, iy, iz);
+        uint64_t sk = ((uint64_t)c->R.htable->hash(ix, iy, iz) << 32) | (uint64_t)(uint32_t)(hp.path * 16u + (hp.code & 15u));
+        uint64_t hw = ((uint64_t)(uint32_t)hp.h << 32) | (uint64_t)(uint32_t)hp.w;
+        memcpy(r + 9, &sk, 8); memcpy(r + 10, &hw, 8); r[11] = 0.0;
+    }
+    return (int64_t)c->canon.size();
+}
+// Replaces the hitpoint set: records in any order are inserted in canonical order (stable sort on the 64-bit sort key).
+int orc_import_hitpoints(void *c_, int64_t n, const double *rec12) {
+    Ctx *c = (Ctx *)c_;
+    const Config &g = c->R.cfg;
+    double r = 200.0 / g.height;
+    if (c->R.htable && c->R.owns_htable) delete c->R.htable;
+    c->R.htable = new Hashtable(g.hashsize, r);
+    c->R.owns_htable = true;
+    std::vector<std::pair<uint64_t, int64_t>> order((size_t)n);
+    for (int64_t i = 0; i < n; i++) { uint64_t sk; memcpy(&sk, rec12 + 12 * i + 9, 8); order[(size_t)i] = {sk, i}; }
+    std::stable_sort(order.begin(), order.end(), [](const std::pair<uint64_t, int64_t> &a, const std::pair<uint64_t, int64_t> &b) { return a.first < b.first; });
+    uint32_t seq = 0;
+    for (auto &o : order) {
+        const double *q = rec12 + 12 * o.second;
+        uint64_t hw; memcpy(&hw, q + 10, 8);
+        Hitpoint hp;
+        hp.pos = v3(q); hp.normal = v3(q + 3); hp.f = v3(q + 6);
+        hp.flux = Vec3(0, 0, 0); hp.r2 = r * r; hp.n = 0;
+        hp.h = (int)(hw >> 32); hp.w = (int)(uint32_t)hw;
+        uint32_t lo = (uint32_t)o.first;
+        hp.code = lo & 15u; hp.path = lo >> 4; hp.seq = seq++;
+        c->R.htable->insert(hp);
+    }
+    c->index();
+    return 0;
+}
+
 // Photons with global indices [first, first+count). nthreads>1 requires U2 (atomic accumulators) + Philox.
 // Returns wall seconds through *seconds.
 int orc_photon_pass(void *c_, uint64_t first, uint64_t count, int nthreads, double *seconds) {

@@ -215,3 +215,70 @@ def test_empty_and_error_paths(gpu):
         assert np.all(g.gather_image(100.0) == 0)
         with pytest.raises(gpu.CgrtError):
             g.commit()
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+# against the committed outputs of the unmodified reference (tests/golden/ref_golden.npz, made by tests/golden/make_golden.py)
+# ---------------------------------------------------------------------------------------------------------------------
+import os  # noqa: E402
+
+GOLDEN = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "ref_golden.npz")
+
+
+def test_hash_keys_vs_reference_golden(gpu):
+    G = np.load(GOLDEN)
+    with gpu.Context(0) as g:
+        for h in (512, 768, 1024, 1080, 4096):
+            k, ixyz = g.hash_keys(G["hash__pos"], 1000001, 200.0 / h)
+            assert np.array_equal(k, G[f"hash_{h}__key"]) and np.array_equal(ixyz, G[f"hash_{h}__ixyz"])
+
+
+@pytest.mark.parametrize("name", ["c1_spheres", "c2_bunny_chess", "c3_dragon_glass", "default_bump", "c4_bump_dof"])
+def test_closest_hit_vs_reference_golden(gpu, name):
+    """t, face-forwarded normal, object id of the reference's own closest-hit loop (main.cpp:50-76) on dumped ray batches.
+    The raw mesh normal / `into` flag follow the GPU's winding rule, compared separately."""
+    G = np.load(GOLDEN)
+    mt = int(G[f"isect_{name}__max_tris"])
+    s = gpu.preset(name, max_tris=None if mt < 0 else mt)
+    with gpu.Context(0, s, gpu.RenderConfig()) as g:
+        a = g.intersect_batch(G[f"isect_{name}__org"], G[f"isect_{name}__dir"])
+        assert np.array_equal(a["obj"], G[f"isect_{name}__obj"])
+        hit = a["obj"] >= 0
+        assert rel_err(a["t"][hit], G[f"isect_{name}__t"][hit]).max() <= T_TOL
+        assert np.abs(a["nrm"][hit] - G[f"isect_{name}__nrm"][hit]).max() <= T_TOL
+        # in fact identical bits except where two coplanar/adjacent triangles tie
+        assert (a["t"][hit] == G[f"isect_{name}__t"][hit]).mean() > 0.999
+        agree = (a["into"][hit] == G[f"isect_{name}__into"][hit]).mean()
+        assert agree > 0.95, agree
+        col = g.surface_color(3 if name == "c1_spheres" else 0, G[f"surf_{name}__pos"])
+        assert np.array_equal(col, G[f"surf_{name}__col"])
+
+
+def test_sharded_renderer_on_gpu_engine(gpu, oracle_lib):
+    """The host-side render() driver (distributed.py) on the product engine, world 1, against the oracle's render."""
+    import torch
+
+    from cgraytracing_b200.distributed import GpuEngine, ShardedRenderer
+
+    s = gpu.preset("c2_bunny_chess")
+    cfg = gpu.RenderConfig(width=96, height=64)
+    with gpu.Context(0, s, cfg) as g:
+        eng = GpuEngine(g, 0)
+        img = ShardedRenderer(eng).render(64, 2, 8000)
+        # export/import round trip of the hitpoint records leaves the grid unchanged
+    with gpu.Context(0, s, cfg) as g2:
+        eng2 = GpuEngine(g2, 0)
+        g2.eye_pass(32, 64); g2.eye_pass(0, 32)
+        rec = eng2.export_hitpoints().clone()
+        eng2.import_hitpoints(rec[torch.randperm(rec.shape[0], device=rec.device)])
+        r2 = ShardedRenderer(eng2)
+        eng2.build_grid()
+        r2.round(8000); r2.round(8000)
+        img2 = eng2.gather_image(16000.0)
+    o = oracle_lib.Oracle(s, cfg)
+    o.eye_pass()
+    for r in range(2):
+        o.photon_pass(r * 8000, 8000); o.round_update()
+    oimg = o.gather_image(16000.0)
+    assert np.allclose(img, oimg, rtol=1e-9, atol=1e-12)
+    assert np.allclose(img2, oimg, rtol=1e-9, atol=1e-12)
