@@ -1,15 +1,16 @@
 #!/usr/bin/env python
 """bench.py — photons/s of the B200 photon-mapping hot path on the configuration the north star names:
-the glass dragon (100,000 triangles) + chessboard floor at 1024x1024, one SPPM round = 16 M photons per GPU
-(BASELINE.json configs[2], "c3_dragon_glass").
+the glass dragon (100,000 triangles) + chessboard floor at 1024x1024, one round = 16 Mi photons per GPU
+(BASELINE.json configs[2], "c3_dragon_glass": 50 rounds x 16M photons).
 
     python bench.py [--gpus N] [--steps K] [--warmup W] [--impl reference]
 
-A *step* is one round of the hot path: trace `--photons` photons per GPU against the persistent hitpoint set
-(emission, closest hit, bounces, 27-cell deposits), all-reduce the accumulators when N > 1, per-round radius/flux update.
-The eye pass / grid build happen once before the timed region (they are reported as eye_rays_per_s); `e2e` measures
-the whole render() through the C ABI from host buffers, H2D of the scene and D2H of the image included.
-Prints ONE JSON line on rank 0.
+A *step* is one round of the hot path: trace `--photons` photons per GPU against the persistent hitpoint set (emission,
+closest hit, bounces, 27-cell deposits), all-reduce the per-hitpoint accumulators when N > 1, per-round radius/flux update.
+`value` times K rounds on the device (inputs resident: scene, BVH, hitpoints, grid). `e2e` times the whole render()
+of the named config through the C ABI from HOST buffers: scene H2D + LBVH build + eye pass + grid + `--e2e-rounds` rounds +
+image D2H, wall clock. `roofline` comes from a separate profiled round of the same run (every kernel launch bracketed by
+CUDA events on the library's stream). Prints ONE JSON line on rank 0.
 """
 from __future__ import annotations
 
@@ -28,8 +29,9 @@ import numpy as np  # noqa: E402
 WORKLOAD = "c3_dragon_glass"
 WIDTH = HEIGHT = 1024
 PHOTONS_PER_ROUND = 16 * 1024 * 1024
+ROUNDS = 50
 
-# algorithmic bytes per unit (device-layout-independent record sizes)
+# algorithmic bytes per unit (layout-independent record sizes)
 B_SEGMENT, B_NODE, B_TRI = 80, 32, 48
 B_CELLS, B_CAND, B_DEP = 27 * 8, 32, 32
 
@@ -80,7 +82,7 @@ class ClockSampler(threading.Thread):
                         self.reasons.add(name)
             except Exception:
                 pass
-            time.sleep(0.1)
+            time.sleep(0.02)
 
     def result(self):
         self.stop_flag = True
@@ -89,6 +91,8 @@ class ClockSampler(threading.Thread):
         return {"sm_mhz": float(np.median(self.samples)), "sm_max_mhz": self.max_mhz, "reasons": sorted(self.reasons), "samples": len(self.samples)}
 
 
+# ---------------------------------------------------------------------------------------------------------------------
+# CPU arms (the only places bench.py touches oracle/)
 # ---------------------------------------------------------------------------------------------------------------------
 def cpu_baseline(scene, cfg, photons, threads=None):
     """The CPU oracle (a line-by-line port of the reference, thread-local Philox, U2 accumulators) on the host cores."""
@@ -114,11 +118,10 @@ def run_reference(args):
     if rank != 0:
         return
     from cgraytracing_b200.scene import RenderConfig, preset
+    from oracle import binding as ob
 
     scene = preset(WORKLOAD)
     cfg = RenderConfig(width=WIDTH, height=HEIGHT, update_mode=1, into_rule=0)
-    from oracle import binding as ob
-
     o = ob.Oracle(scene, cfg)
     threads = o.max_threads()
     o.eye_pass()
@@ -136,25 +139,22 @@ def run_reference(args):
         "warmup": args.warmup, "ms_per_step": 1e3 * total / len(times), "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
         "dtype": "f64", "data": "synthetic",
         "config": {"workload": WORKLOAD, "width": WIDTH, "height": HEIGHT, "photons_per_step": sample,
-                   "note": "bounded CPU sample of the same round; throughput is per photon and stationary"},
+                   "note": "bounded CPU sample of the same round; cost per photon is stationary"},
         "cpu_baseline": {"value": v, "unit": "photons/s", "cores": threads, "kind": "port",
-                         "sample": f"{sample} photons per step x {args.steps} steps, oracle port of main.cpp trace()/render(), {threads} OpenMP threads"},
+                         "sample": f"{sample} photons per step x {args.steps} steps, oracle port of main.cpp trace()/render() "
+                                   f"(pinned bit-exact to the compiled reference), {threads} OpenMP threads"},
         "e2e": {"value": v, "unit": "photons/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }
     print(json.dumps(line), flush=True)
 
 
 # ---------------------------------------------------------------------------------------------------------------------
-class _DevArray:
-    def __init__(self, ptr, n, typestr):
-        self.__cuda_array_interface__ = {"shape": (n,), "typestr": typestr, "data": (ptr, False), "version": 2}
-
-
 def run_gpu(args):
     import torch
     import torch.distributed as dist
 
     from cgraytracing_b200 import Context, RenderConfig, preset
+    from cgraytracing_b200.distributed import GpuEngine, ShardedRenderer
 
     world = int(os.environ.get("WORLD_SIZE", "1"))
     rank = int(os.environ.get("RANK", "0"))
@@ -167,28 +167,18 @@ def run_gpu(args):
     P = args.photons
     peak, peak_src = load_peaks()
 
-    # ---- setup (untimed for `value`): scene upload + LBVH build, eye pass, grid
+    # ---- setup (untimed for `value`): scene upload + LBVH build, tile-sharded eye pass + all-gather, grid
     g = Context(local)
     g.set_config(cfg, accum_mode=args.accum)
     scene.build_into(g)
     t0 = time.time()
     g.commit()
     t_commit = time.time() - t0
-    g.eye_pass()
-    g.build_grid()
+    eng = GpuEngine(g, local)
+    R = ShardedRenderer(eng, rank, world)
+    R.eye(HEIGHT)
     tm0 = g.timings()
     c0 = g.counters()
-    eye_rays_per_s = c0["eye_segments"] / (tm0["eye"] * 1e-3)
-    acc_ptr, acc_n = g.accum_dev()
-    acc_t = torch.as_tensor(_DevArray(acc_ptr, acc_n, "<f8" if args.accum == 0 else "<f4"), device=f"cuda:{local}") if acc_n else None
-    stream = torch.cuda.ExternalStream(g.stream())
-
-    def step(r):
-        g.photon_pass((r * world + rank) * P, P)
-        if world > 1 and acc_t is not None:
-            dist.all_reduce(acc_t)
-            torch.cuda.current_stream().synchronize()
-        g.round_update()
 
     # ---- roofline accounting (outside the timed region): counting build of the same traversal on a sample
     per_seg_nodes = per_seg_tris = None
@@ -197,30 +187,33 @@ def run_gpu(args):
             gc.set_config(cfg, accum_mode=args.accum)
             scene.build_into(gc); gc.commit(); gc.eye_pass(); gc.build_grid()
             gc.set_counting(True)
-            gc.photon_pass(0, 1 << 18)
+            gc.photon_pass(0, 1 << 20)
             cc = gc.counters()
             per_seg_nodes = cc["node_visits"] / cc["photon_segments"]
             per_seg_tris = cc["tri_tests"] / cc["photon_segments"]
 
-    for w in range(args.warmup):
-        step(w)
+    for _ in range(args.warmup):
+        R.round(world * P)
+    g.synchronize()
     if world > 1:
         dist.barrier()
     torch.cuda.synchronize()
     sampler = ClockSampler(local)
     sampler.start()
-    tm1, c1 = g.timings(), g.counters()
+    c1 = g.counters()
+    stream = torch.cuda.ExternalStream(g.stream())
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record(stream)
-    for k in range(args.steps):
-        step(args.warmup + k)
+    for _ in range(args.steps):
+        R.round(world * P)
     e1.record(stream)
+    g.synchronize()
     torch.cuda.synchronize()
     if world > 1:
         dist.barrier()
     clocks = sampler.result()
     ms = e0.elapsed_time(e1)
-    tm2, c2 = g.timings(), g.counters()
+    c2 = g.counters()
     if world > 1:
         t = torch.tensor([ms], device=f"cuda:{local}", dtype=torch.float64)
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
@@ -228,46 +221,69 @@ def run_gpu(args):
     total_photons = world * P * args.steps
     value = total_photons / (ms * 1e-3)
 
+    # ---- one profiled round (every launch bracketed by events on the ctx stream): per-kernel durations for the roofline
+    g.set_profiling(True)
+    tp0, cp0 = g.timings(), g.counters()
+    R.round(world * P)
+    g.synchronize()
+    tp1, cp1 = g.timings(), g.counters()
+    g.set_profiling(False)
+
     if rank != 0:
         if world > 1:
             dist.destroy_process_group()
         return
 
-    # ---- per-kernel numbers of the timed region (CUDA events recorded on the ctx stream inside the library)
-    seg = c2["photon_segments"] - c1["photon_segments"]
-    hits = c2["diffuse_hits"] - c1["diffuse_hits"]
-    cand = c2["candidates"] - c1["candidates"]
-    dep = c2["deposits"] - c1["deposits"]
-    t_trace = (tm2["photon_trace"] - tm1["photon_trace"]) * 1e-3
-    t_dep = (tm2["photon_deposit"] - tm1["photon_deposit"]) * 1e-3
-    n_launch_trace = args.steps * 5 * ((P + (4 << 20) - 1) // (4 << 20))
+    seg = cp1["photon_segments"] - cp0["photon_segments"]
+    hits = cp1["diffuse_hits"] - cp0["diffuse_hits"]
+    cand = cp1["candidates"] - cp0["candidates"]
+    dep = cp1["deposits"] - cp0["deposits"]
+    t_trace = (tp1["photon_trace"] - tp0["photon_trace"]) * 1e-3
+    t_dep = (tp1["photon_deposit"] - tp0["photon_deposit"]) * 1e-3
+    t_upd = (tp1["update"] - tp0["update"]) * 1e-3
+    n_launch = (P + (4 << 20) - 1) // (4 << 20)
     bytes_trace = seg * (B_SEGMENT + B_NODE * per_seg_nodes + B_TRI * per_seg_tris)
     bytes_dep = hits * B_CELLS + cand * B_CAND + dep * B_DEP
     kernels = {
-        "photon_trace_kernel": {"seconds": t_trace, "alg_bytes": bytes_trace, "gbps": bytes_trace / t_trace / 1e9, "launches": n_launch_trace,
-                                "nodes_per_segment": per_seg_nodes, "tris_per_segment": per_seg_tris, "segments_per_s": seg / t_trace},
-        "photon_deposit_kernel": {"seconds": t_dep, "alg_bytes": bytes_dep, "gbps": bytes_dep / t_dep / 1e9, "launches": n_launch_trace,
-                                  "candidates_per_hit": cand / max(1, hits), "deposits_per_hit": dep / max(1, hits), "hits_per_s": hits / t_dep},
+        "photon_trace_kernel": {"seconds": t_trace, "alg_bytes": bytes_trace, "gbps": bytes_trace / t_trace / 1e9, "launches": n_launch,
+                                "ms_per_launch": 1e3 * t_trace / n_launch, "nodes_per_segment": per_seg_nodes, "tris_per_segment": per_seg_tris,
+                                "segments_per_s": seg / t_trace},
+        "photon_deposit_kernel": {"seconds": t_dep, "alg_bytes": bytes_dep, "gbps": bytes_dep / t_dep / 1e9, "launches": n_launch,
+                                  "ms_per_launch": 1e3 * t_dep / n_launch, "candidates_per_hit": cand / max(1, hits),
+                                  "deposits_per_hit": dep / max(1, hits), "hits_per_s": hits / t_dep},
+        "round_update_kernel": {"seconds": t_upd, "launches": 1},
     }
     dom = "photon_trace_kernel" if t_trace >= t_dep else "photon_deposit_kernel"
     roofline = {"bound": "hbm", "kernel": dom, "achieved": kernels[dom]["gbps"], "peak": peak, "unit": "GB/s", "frac": kernels[dom]["gbps"] / peak,
-                "traffic": None, "peak_source": peak_src, "share_of_step": kernels[dom]["seconds"] / (ms * 1e-3),
-                "note": "algorithmic bytes per SURVEY 8(d) record sizes; working set (BVH 16 MB, hitpoints 80 MB) is L2-resident, so this is an L2/latency-bound kernel measured against the HBM copy peak"}
+                "traffic": None, "peak_source": peak_src, "share_of_step": kernels[dom]["seconds"] / (t_trace + t_dep + t_upd),
+                "other_kernel": {k: {"achieved": v["gbps"], "frac": v["gbps"] / peak} for k, v in kernels.items() if k != dom and "gbps" in v},
+                "note": "algorithmic bytes per SURVEY 8(d) record sizes x counters of the profiled round / CUDA-event durations; the working set "
+                        "(BVH 16 MB, hitpoint prefilter 18 MB + exact records 72 MB, cell table 4 MB) is L2-resident, so the algorithmic "
+                        "rate may exceed the DRAM rate; peak is the measured HBM copy bandwidth"}
 
-    # ---- e2e: the whole render() through the C ABI from host buffers (scene H2D + LBVH + eye pass + grid + one round + image D2H)
+    # ---- e2e: the whole render() of the named config through the C ABI from host buffers
     scene_bytes = sum(o["tri9"].nbytes for o in scene.objects if o["kind"] == "mesh") + sum(t["rgb"].nbytes for t in scene.textures)
-    e2e_steps = max(1, min(args.steps, 3))
-    t0 = time.time()
-    for k in range(e2e_steps):
-        with Context(local) as ge:
-            ge.set_config(cfg, accum_mode=args.accum)
-            scene.build_into(ge); ge.commit(); ge.eye_pass(); ge.build_grid()
-            ge.photon_pass(k * P, P)
-            ge.round_update()
-            img, rgb8 = ge.gather_image(float(P), want_rgb8=True)
-    t_e2e = (time.time() - t0) / e2e_steps
-    e2e = {"value": P / t_e2e, "unit": "photons/s", "h2d_bytes_per_step": int(scene_bytes), "d2h_bytes_per_step": int(img.nbytes + rgb8.nbytes),
-           "seconds_per_step": t_e2e, "what": "cgrt_create + scene upload + LBVH build + eye pass + grid + one 16M-photon round + update + image download, wall clock"}
+    e2e = None
+    if args.e2e_rounds > 0 and world == 1:
+        def render_once(rounds):
+            t0 = time.time()
+            with Context(local) as ge:
+                ge.set_config(cfg, accum_mode=args.accum)
+                scene.build_into(ge); ge.commit(); ge.eye_pass(); ge.build_grid()
+                for k in range(rounds):
+                    ge.photon_pass(k * P, P)
+                    ge.round_update()
+                img, rgb8 = ge.gather_image(float(P) * rounds, want_rgb8=True)
+            return time.time() - t0, img, rgb8
+
+        render_once(1)  # warm-up (memory pool, module load)
+        t1, img, rgb8 = render_once(1)
+        tN, img, rgb8 = render_once(args.e2e_rounds)
+        e2e = {"value": P * args.e2e_rounds / tN, "unit": "photons/s", "h2d_bytes_per_step": int(scene_bytes),
+               "d2h_bytes_per_step": int(img.nbytes + rgb8.nbytes), "seconds_per_step": tN, "rounds_per_step": args.e2e_rounds,
+               "one_round_render": {"value": P / t1, "seconds": t1},
+               "what": f"one step = one whole render() of {WORKLOAD}: cgrt_create + scene upload from host arrays + LBVH build + eye pass + "
+                       f"grid + {args.e2e_rounds} rounds x {P} photons + updates + fp64 image and 8-bit image download, wall clock"}
 
     # ---- CPU baseline beside it (bounded sample)
     cpu = cpu_baseline(scene, RenderConfig(width=WIDTH, height=HEIGHT, update_mode=1, into_rule=0), args.cpu_photons) if args.cpu_photons > 0 else None
@@ -277,8 +293,9 @@ def run_gpu(args):
         "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
         "config": {"workload": WORKLOAD, "width": WIDTH, "height": HEIGHT, "photons_per_gpu_per_step": P, "hitpoints": c2["hitpoints"],
                    "triangles": scene.num_triangles(), "accum": "f64 atomics" if args.accum == 0 else "v4.f32 red",
-                   "l2": "inputs larger than L2: each round streams fresh ray/deposit queues (>1.5 GB) and new photons"},
-        "s_per_round": ms * 1e-3 / args.steps, "eye_rays_per_s": eye_rays_per_s, "segments_per_s": seg * world / (ms * 1e-3),
+                   "l2": "inputs larger than L2: every round streams a fresh 1.5 GB deposit queue per 4 Mi-photon chunk and new photons"},
+        "s_per_round": ms * 1e-3 / args.steps, "eye_rays_per_s": c0["eye_segments"] / (tm0["eye"] * 1e-3),
+        "segments_per_s": (c2["photon_segments"] - c1["photon_segments"]) * world / (ms * 1e-3),
         "setup": {"commit_s": t_commit, "eye_ms": tm0["eye"], "grid_ms": tm0["grid"], "eye_segments": c0["eye_segments"]},
         "roofline": roofline, "kernels": kernels, "cpu_baseline": cpu, "clocks": clocks, "e2e": e2e,
         "gpu_launches": int(c2["gpu_launches"] - c1["gpu_launches"]),
@@ -291,13 +308,14 @@ def run_gpu(args):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=3)
+    ap.add_argument("--steps", type=int, default=5)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--photons", type=int, default=PHOTONS_PER_ROUND, help="photons per GPU per step (the named config uses 16 Mi)")
-    ap.add_argument("--accum", type=int, default=0, help="0: fp64 atomics, 1: v4.f32 red")
+    ap.add_argument("--accum", type=int, default=1, help="0: fp64 atomics, 1: one v4.f32 red per deposit (SURVEY 8e: float32 x4 accumulators)")
     ap.add_argument("--cpu-photons", type=int, default=400000, help="photon budget of the CPU baseline sample (0 = skip)")
     ap.add_argument("--ref-photons", type=int, default=200000, help="photons per step of --impl reference")
+    ap.add_argument("--e2e-rounds", type=int, default=ROUNDS, help="rounds of the end-to-end render() (the named config has 50; 0 = skip)")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)

@@ -36,6 +36,15 @@ struct BvhBuild {
     int ntris = 0;
 };
 
+// ping-pong buffers of the radix sort
+template <typename K>
+struct SortScratch {
+    K *kb[2] = {nullptr, nullptr};
+    uint32_t *vb[2] = {nullptr, nullptr};
+    uint32_t *counts = nullptr;
+    size_t cap = 0;
+};
+
 }  // namespace
 
 struct cgrt_ctx {
@@ -63,17 +72,27 @@ struct cgrt_ctx {
     uint32_t *cell_start = nullptr, *pix_start = nullptr, *pix_perm = nullptr;
 
     // queues
-    RayQueue q[2];
-    DepositQueue dq;
-    unsigned int q_cap = 0, dq_cap = 0;
-    unsigned int *d_qcount = nullptr;  // [0],[1]: ray queues, [2]: deposit queue
+    RayQueue q[2];       // eye pass only: the photon pass keeps its rays in registers
+    unsigned int q_cap = 0;
+    unsigned int *d_qcount = nullptr;  // [0],[1]: eye ray queues; [2..7]: suspended-photon queues of the photon pass
+    // photon pass buffers
+    DepositRec *dep_rec = nullptr;
+    uint32_t *dep_keys = nullptr;
+    size_t dep_cap = 0;          // deposit slots
+    PhotonState *pq[2] = {nullptr, nullptr};
+    size_t pq_cap = 0;
+    uint32_t *dep_perm = nullptr;     // cell-grouped order of the valid slots
+    uint32_t *dep_hist = nullptr;     // CGRT_NBINS bin counters -> cursors
+    uint32_t *dep_bsum = nullptr;     // per-4096-bin block totals
+    uint32_t *dep_nvalid = nullptr;
     Counters *d_ctr = nullptr;
     TravCounters *d_tc = nullptr;
     uint64_t launches = 0;
-    uint64_t diffuse_hits = 0;
+    unsigned int deposit_grid = 148 * 8;  // resident deposit blocks: 8 x 256 threads per SM
+    int profiling = 0;   // 1: time every photon kernel with events (serialises host and device at the end of each pass)
     double ms[8] = {0, 0, 0, 0, 0, 0, 0, 0};
     cudaEvent_t ev[2] = {nullptr, nullptr};
-    size_t photon_chunk = 4u << 20;
+    size_t photon_chunk = 16u << 20;  // photons per trace launch: bounds the deposit table (chunk * max_depth * 100 B)
     int counting = 0;  // 1: photon trace kernels also count BVH node visits / triangle tests (roofline accounting)
 };
 
@@ -104,7 +123,7 @@ template <typename T>
 int dalloc(cgrt_ctx *ctx, T **p, size_t n) {
     *p = nullptr;
     if (n == 0) n = 1;
-    CK(cudaMalloc((void **)p, n * sizeof(T)));
+    CK(cudaMallocAsync((void **)p, n * sizeof(T), ctx->stream));  // stream-ordered pool: no device-wide sync, memory is reused
     ctx->allocs.push_back((void *)*p);
     return 0;
 }
@@ -116,7 +135,7 @@ int dfree(cgrt_ctx *ctx, void *p) {
             ctx->allocs.pop_back();
             break;
         }
-    CK(cudaFree(p));
+    CK(cudaFreeAsync(p, ctx->stream));
     return 0;
 }
 inline unsigned int nblk(size_t n, unsigned int b) { return (unsigned int)((n + b - 1) / b); }
@@ -124,8 +143,12 @@ inline unsigned int nblk(size_t n, unsigned int b) { return (unsigned int)((n + 
 struct PhaseTimer {
     cgrt_ctx *ctx;
     int slot;
-    PhaseTimer(cgrt_ctx *c, int s) : ctx(c), slot(s) { cudaEventRecord(ctx->ev[0], ctx->stream); }
+    bool on;
+    PhaseTimer(cgrt_ctx *c, int s, bool enabled = true) : ctx(c), slot(s), on(enabled) {
+        if (on) cudaEventRecord(ctx->ev[0], ctx->stream);
+    }
     void stop() {
+        if (!on) return;
         cudaEventRecord(ctx->ev[1], ctx->stream);
         cudaEventSynchronize(ctx->ev[1]);
         float t = 0;
@@ -135,39 +158,60 @@ struct PhaseTimer {
 };
 
 // ---- radix sort driver: keys (dev) -> sorted keys + permutation (dev). nbits rounded up to whole 8-bit digits.
-int radix_sort_dev(cgrt_ctx *ctx, size_t n, const uint64_t *keys_in, int nbits, uint64_t *keys_out, uint32_t *perm_out) {
-    if (n == 0) return 0;
+// `scratch` (optional) supplies the ping-pong buffers so that a hot caller (the per-round deposit sort) allocates nothing.
+template <typename K>
+int sort_scratch_reserve(cgrt_ctx *ctx, SortScratch<K> &sc, size_t n) {
+    if (n <= sc.cap) return 0;
+    if (sc.cap) { CKS(dfree(ctx, sc.kb[0])); CKS(dfree(ctx, sc.kb[1])); CKS(dfree(ctx, sc.vb[0])); CKS(dfree(ctx, sc.vb[1])); CKS(dfree(ctx, sc.counts)); }
+    size_t ntiles = (n + RS_TILE - 1) / RS_TILE;
+    CKS(dalloc(ctx, &sc.kb[0], n)); CKS(dalloc(ctx, &sc.kb[1], n)); CKS(dalloc(ctx, &sc.vb[0], n)); CKS(dalloc(ctx, &sc.vb[1], n));
+    CKS(dalloc(ctx, &sc.counts, (size_t)256 * ntiles));
+    sc.cap = n;
+    return 0;
+}
+template <typename K>
+int sort_scratch_release(cgrt_ctx *ctx, SortScratch<K> &sc) {
+    if (!sc.cap) return 0;
+    CKS(dfree(ctx, sc.kb[0])); CKS(dfree(ctx, sc.kb[1])); CKS(dfree(ctx, sc.vb[0])); CKS(dfree(ctx, sc.vb[1])); CKS(dfree(ctx, sc.counts));
+    sc = SortScratch<K>();
+    return 0;
+}
+// Asynchronous on the ctx stream. Results are left in the scratch buffers: *keys_sorted / *perm point at them.
+template <typename K>
+int radix_sort_async(cgrt_ctx *ctx, SortScratch<K> &sc, size_t n, const K *keys_in, int nbits, const K **keys_sorted, const uint32_t **perm) {
     if (n >= (1ull << 32)) FAIL(CGRT_ERR_CAPACITY, "radix sort: more than 2^32 keys");
+    CKS(sort_scratch_reserve(ctx, sc, n));
     int passes = (nbits + 7) / 8;
     if (passes < 1) passes = 1;
     int ntiles = (int)((n + RS_TILE - 1) / RS_TILE);
-    uint64_t *kb[2];
-    uint32_t *vb[2];
-    uint32_t *counts;
-    CKS(dalloc(ctx, &kb[0], n));
-    CKS(dalloc(ctx, &kb[1], n));
-    CKS(dalloc(ctx, &vb[0], n));
-    CKS(dalloc(ctx, &vb[1], n));
-    CKS(dalloc(ctx, &counts, (size_t)256 * ntiles));
-    const uint64_t *src_k = keys_in;
+    const K *src_k = keys_in;
     const uint32_t *src_v = nullptr;
     int cur = 0;
     for (int p = 0; p < passes; p++) {
         int shift = 8 * p;
-        rs_hist_kernel<<<ntiles, RS_THREADS, 0, ctx->stream>>>(src_k, (int64_t)n, shift, counts, ntiles);
-        rs_scan_kernel<<<1, 1024, 0, ctx->stream>>>(counts, (int64_t)256 * ntiles);
-        rs_scatter_kernel<<<ntiles, RS_THREADS, 0, ctx->stream>>>(src_k, src_v, kb[cur], vb[cur], (int64_t)n, shift, counts, ntiles, p == 0);
+        rs_hist_kernel<K><<<ntiles, RS_THREADS, 0, ctx->stream>>>(src_k, (int64_t)n, shift, sc.counts, ntiles);
+        rs_scan_kernel<<<1, 1024, 0, ctx->stream>>>(sc.counts, (int64_t)256 * ntiles);
+        rs_scatter_kernel<K><<<ntiles, RS_THREADS, 0, ctx->stream>>>(src_k, src_v, sc.kb[cur], sc.vb[cur], (int64_t)n, shift, sc.counts, ntiles, p == 0);
         ctx->launches += 3;
-        src_k = kb[cur];
-        src_v = vb[cur];
+        src_k = sc.kb[cur];
+        src_v = sc.vb[cur];
         cur ^= 1;
     }
-    CK(cudaMemcpyAsync(keys_out, src_k, n * sizeof(uint64_t), cudaMemcpyDeviceToDevice, ctx->stream));
-    CK(cudaMemcpyAsync(perm_out, src_v, n * sizeof(uint32_t), cudaMemcpyDeviceToDevice, ctx->stream));
-    CK(cudaStreamSynchronize(ctx->stream));
     CK(cudaGetLastError());
-    CKS(dfree(ctx, kb[0])); CKS(dfree(ctx, kb[1])); CKS(dfree(ctx, vb[0])); CKS(dfree(ctx, vb[1])); CKS(dfree(ctx, counts));
+    *keys_sorted = src_k;
+    *perm = src_v;
     return 0;
+}
+int radix_sort_dev(cgrt_ctx *ctx, size_t n, const uint64_t *keys_in, int nbits, uint64_t *keys_out, uint32_t *perm_out) {
+    if (n == 0) return 0;
+    SortScratch<uint64_t> sc;
+    const uint64_t *ks;
+    const uint32_t *pm;
+    CKS(radix_sort_async(ctx, sc, n, keys_in, nbits, &ks, &pm));
+    CK(cudaMemcpyAsync(keys_out, ks, n * sizeof(uint64_t), cudaMemcpyDeviceToDevice, ctx->stream));
+    CK(cudaMemcpyAsync(perm_out, pm, n * sizeof(uint32_t), cudaMemcpyDeviceToDevice, ctx->stream));
+    CK(cudaStreamSynchronize(ctx->stream));
+    return sort_scratch_release(ctx, sc);
 }
 
 // ---- LBVH build over n triangles already on the device (tri9, original order)
@@ -220,8 +264,15 @@ int build_bvh(cgrt_ctx *ctx, double *tri9_dev, int n, double orient_sign, int sl
         lbvh_pack_kernel<<<nblk(ninternal, T), T, 0, ctx->stream>>>(n, left, right, box, nodes);
         ctx->launches += 3;
     }
+    float root[6];  // box 0 is the root (the only leaf when n == 1)
+    CK(cudaMemcpyAsync(root, box, sizeof root, cudaMemcpyDeviceToHost, ctx->stream));
     CK(cudaStreamSynchronize(ctx->stream));
     CK(cudaGetLastError());
+    B.f32_ok = 1;
+    for (int a = 0; a < 3; a++) {
+        B.root_lo[a] = root[a]; B.root_hi[a] = root[3 + a];
+        if (!(std::fabs(root[a]) <= CGRT_F32_BOUND && std::fabs(root[3 + a]) <= CGRT_F32_BOUND)) B.f32_ok = 0;
+    }
     B.nodes = nodes;
     B.tris = tris;
     B.tri_id = tri_id;
@@ -259,19 +310,31 @@ int free_queue(cgrt_ctx *ctx, RayQueue &q) {
 }
 int ensure_queues(cgrt_ctx *ctx, size_t cap) {
     if (cap <= ctx->q_cap) return 0;
-    if (ctx->q_cap) {
-        CKS(free_queue(ctx, ctx->q[0])); CKS(free_queue(ctx, ctx->q[1]));
-        CKS(dfree(ctx, ctx->dq.px));
-    }
+    if (ctx->q_cap) { CKS(free_queue(ctx, ctx->q[0])); CKS(free_queue(ctx, ctx->q[1])); }
     CKS(alloc_queue(ctx, ctx->q[0], cap, true));
     CKS(alloc_queue(ctx, ctx->q[1], cap, true));
-    double *base;
-    CKS(dalloc(ctx, &base, cap * 9));
-    DepositQueue &d = ctx->dq;
-    d.px = base; d.py = base + cap; d.pz = base + 2 * cap; d.nx = base + 3 * cap; d.ny = base + 4 * cap; d.nz = base + 5 * cap;
-    d.fx = base + 6 * cap; d.fy = base + 7 * cap; d.fz = base + 8 * cap;
     ctx->q_cap = (unsigned int)cap;
-    ctx->dq_cap = (unsigned int)cap;
+    return 0;
+}
+int ensure_photon_buffers(cgrt_ctx *ctx, size_t photons, size_t slots) {
+    if (slots > ctx->dep_cap) {
+        if (ctx->dep_cap) { CKS(dfree(ctx, ctx->dep_rec)); CKS(dfree(ctx, ctx->dep_keys)); CKS(dfree(ctx, ctx->dep_perm)); }
+        CKS(dalloc(ctx, &ctx->dep_rec, slots));
+        CKS(dalloc(ctx, &ctx->dep_keys, slots));
+        CKS(dalloc(ctx, &ctx->dep_perm, slots));
+        ctx->dep_cap = slots;
+    }
+    if (photons > ctx->pq_cap) {
+        if (ctx->pq_cap) { CKS(dfree(ctx, ctx->pq[0])); CKS(dfree(ctx, ctx->pq[1])); }
+        CKS(dalloc(ctx, &ctx->pq[0], photons));
+        CKS(dalloc(ctx, &ctx->pq[1], photons));
+        ctx->pq_cap = photons;
+    }
+    if (!ctx->dep_hist) {
+        CKS(dalloc(ctx, &ctx->dep_hist, (size_t)CGRT_NBINS));
+        CKS(dalloc(ctx, &ctx->dep_bsum, (size_t)CGRT_NBINS / (CGRT_SCAN_BLOCK * CGRT_SCAN_ITEMS)));
+        CKS(dalloc(ctx, &ctx->dep_nvalid, 1));
+    }
     return 0;
 }
 
@@ -347,25 +410,36 @@ int cgrt_create(int device, cgrt_ctx **out) {
     if (cudaSetDevice(device) != cudaSuccess) return CGRT_ERR_NO_DEVICE;
     cgrt_ctx *ctx = new cgrt_ctx();
     ctx->device = device;
+    {
+        int sms = 0;
+        if (cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, device) == cudaSuccess && sms > 0) ctx->deposit_grid = (unsigned int)sms * 8u;
+    }
     cgrt_default_config(&ctx->cfg);
     derive_params(ctx);
     memset(&ctx->S, 0, sizeof ctx->S);
     memset(&ctx->A, 0, sizeof ctx->A);
     memset(ctx->q, 0, sizeof ctx->q);
-    memset(&ctx->dq, 0, sizeof ctx->dq);
+    {   // keep freed blocks in the device's default pool instead of returning them to the OS at every synchronize
+        cudaMemPool_t pool;
+        if (cudaDeviceGetDefaultMemPool(&pool, device) == cudaSuccess) {
+            uint64_t keep = UINT64_MAX;
+            cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &keep);
+        }
+    }
     if (cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking) != cudaSuccess || cudaEventCreate(&ctx->ev[0]) != cudaSuccess ||
         cudaEventCreate(&ctx->ev[1]) != cudaSuccess) {
         delete ctx;
         return CGRT_ERR_CUDA;
     }
-    if (dalloc(ctx, &ctx->d_hp_count, 1) || dalloc(ctx, &ctx->d_qcount, 4) || dalloc(ctx, &ctx->d_ctr, 1) || dalloc(ctx, &ctx->d_tc, 1)) {
+    if (dalloc(ctx, &ctx->d_hp_count, 1) || dalloc(ctx, &ctx->d_qcount, 8) || dalloc(ctx, &ctx->d_ctr, 1) || dalloc(ctx, &ctx->d_tc, 1)) {
         delete ctx;
         return CGRT_ERR_CUDA;
     }
-    cudaMemset(ctx->d_hp_count, 0, sizeof(unsigned int));
-    cudaMemset(ctx->d_qcount, 0, 4 * sizeof(unsigned int));
-    cudaMemset(ctx->d_ctr, 0, sizeof(Counters));
-    cudaMemset(ctx->d_tc, 0, sizeof(TravCounters));
+    cudaMemsetAsync(ctx->d_hp_count, 0, sizeof(unsigned int), ctx->stream);
+    cudaMemsetAsync(ctx->d_qcount, 0, 8 * sizeof(unsigned int), ctx->stream);
+    cudaMemsetAsync(ctx->d_ctr, 0, sizeof(Counters), ctx->stream);
+    cudaMemsetAsync(ctx->d_tc, 0, sizeof(TravCounters), ctx->stream);
+    cudaStreamSynchronize(ctx->stream);
     *out = ctx;
     return CGRT_OK;
 }
@@ -374,7 +448,8 @@ int cgrt_destroy(cgrt_ctx *ctx) {
     if (!ctx) return CGRT_OK;
     cudaSetDevice(ctx->device);
     cudaStreamSynchronize(ctx->stream);
-    for (void *p : ctx->allocs) cudaFree(p);
+    for (void *p : ctx->allocs) cudaFreeAsync(p, ctx->stream);
+    cudaStreamSynchronize(ctx->stream);
     if (ctx->ev[0]) cudaEventDestroy(ctx->ev[0]);
     if (ctx->ev[1]) cudaEventDestroy(ctx->ev[1]);
     if (ctx->stream) cudaStreamDestroy(ctx->stream);
@@ -646,6 +721,7 @@ int cgrt_object_triangles(cgrt_ctx *ctx, int obj, double *tri9, int64_t cap, int
     *ntri = b < 0 ? 0 : ctx->bvh_src[b].ntris;
     if (tri9 && b >= 0) {
         int64_t n = *ntri < cap ? *ntri : cap;
+        CK(cudaStreamSynchronize(ctx->stream));
         CK(cudaMemcpy(tri9, ctx->bvh_src[b].tri9, (size_t)n * 9 * sizeof(double), cudaMemcpyDeviceToHost));
     }
     return CGRT_OK;
@@ -694,7 +770,7 @@ int cgrt_eye_pass(cgrt_ctx *ctx, int y0, int y1) {
         size_t n = (size_t)(r1 - r0) * per_row;
         int cur = 0;
         for (int depth = 0; depth < P.max_depth && n > 0; depth++) {
-            CKS(ensure_queues(ctx, 2 * n > ctx->photon_chunk ? 2 * n : ctx->photon_chunk));
+            CKS(ensure_queues(ctx, 2 * n > max_rays ? 2 * n : max_rays));
             CKS(ensure_hp_capacity(ctx, (size_t)ctx->hp_count + n));
             CK(cudaMemsetAsync(ctx->d_qcount + (cur ^ 1), 0, sizeof(unsigned int), ctx->stream));
             if (depth == 0)
@@ -752,6 +828,7 @@ int cgrt_build_grid(cgrt_ctx *ctx) {
     CKS(dalloc(ctx, &ctx->cell_start, (size_t)P.hashsize + 1));
     CKS(dalloc(ctx, &ctx->pix_start, npix + 1));
     CKS(dalloc(ctx, &ctx->pix_perm, (size_t)n));
+    CKS(dalloc(ctx, &ctx->A.pre, (size_t)n));
     CKS(dalloc(ctx, &ctx->A.hot, (size_t)n));
     CKS(dalloc(ctx, &ctx->A.f, (size_t)n * 4));
     CKS(dalloc(ctx, &ctx->A.flux, (size_t)n * 4));
@@ -801,60 +878,87 @@ int cgrt_build_grid(cgrt_ctx *ctx) {
 }
 
 // ---- photon pass ---------------------------------------------------------------------------------------------------
+// Per chunk: max_depth trace launches (the first emits and runs the analytic fast path, the others resume the photons that
+// were suspended in front of a mesh), a 24-bit radix sort of the deposit keys, and the cell-grouped deposit kernel. No host
+// synchronisation anywhere: the pass is asynchronous on the ctx stream unless profiling is on (then the phases are
+// bracketed by events and the pass ends with one synchronise).
 int cgrt_photon_pass(cgrt_ctx *ctx, uint64_t first, uint64_t count) {
     if (!ctx) return CGRT_ERR_INVALID;
     if (!ctx->grid_built) FAIL(CGRT_ERR_INVALID, "build the grid first");
     CK(cudaSetDevice(ctx->device));
     const PassParams &P = ctx->P;
-    CKS(ensure_queues(ctx, ctx->photon_chunk));
-    cudaEvent_t e0, e1, e2;
-    CK(cudaEventCreate(&e0)); CK(cudaEventCreate(&e1)); CK(cudaEventCreate(&e2));
-    for (uint64_t done = 0; done < count; done += ctx->photon_chunk) {
-        size_t n = (size_t)((count - done) < ctx->photon_chunk ? (count - done) : ctx->photon_chunk);
-        uint64_t base = first + done;
-        int cur = 0;
-        for (int depth = 0; depth < P.max_depth && n > 0; depth++) {
-            CK(cudaMemsetAsync(ctx->d_qcount + (cur ^ 1), 0, sizeof(unsigned int), ctx->stream));
-            CK(cudaMemsetAsync(ctx->d_qcount + 2, 0, sizeof(unsigned int), ctx->stream));
-            CK(cudaEventRecord(e0, ctx->stream));
-#define LAUNCH_PT(F, C)                                                                                                                  \
-    photon_trace_kernel<F, C><<<nblk(n, 128), 128, 0, ctx->stream>>>(ctx->S, P, depth, ctx->q[cur], (unsigned int)n, base, ctx->q[cur ^ 1], \
-                                                                     ctx->d_qcount + (cur ^ 1), ctx->dq, ctx->d_qcount + 2, ctx->d_ctr, ctx->d_tc)
-            if (ctx->counting) { if (depth == 0) LAUNCH_PT(true, true); else LAUNCH_PT(false, true); }
-            else { if (depth == 0) LAUNCH_PT(true, false); else LAUNCH_PT(false, false); }
-#undef LAUNCH_PT
-            ctx->launches++;
-            CK(cudaEventRecord(e1, ctx->stream));
-            unsigned int counts[2];
-            CK(cudaMemcpyAsync(&counts[0], ctx->d_qcount + (cur ^ 1), sizeof(unsigned int), cudaMemcpyDeviceToHost, ctx->stream));
-            CK(cudaMemcpyAsync(&counts[1], ctx->d_qcount + 2, sizeof(unsigned int), cudaMemcpyDeviceToHost, ctx->stream));
-            CK(cudaStreamSynchronize(ctx->stream));
-            CK(cudaGetLastError());
-            unsigned int ndq = counts[1];
-            if (ndq > 0 && ctx->nhp > 0) {
-                unsigned int blocks = nblk((size_t)ndq * 32, 256);
-                unsigned int maxb = 148 * 8 * 4;
-                if (blocks > maxb) blocks = maxb;
-                if (ctx->cfg.accum_mode == 0)
-                    photon_deposit_kernel<0><<<blocks, 256, 0, ctx->stream>>>(P, ctx->dq, ndq, ctx->cell_start, ctx->A.hot, ctx->A.f, ctx->acc, ctx->d_ctr);
-                else
-                    photon_deposit_kernel<1><<<blocks, 256, 0, ctx->stream>>>(P, ctx->dq, ndq, ctx->cell_start, ctx->A.hot, ctx->A.f, ctx->acc, ctx->d_ctr);
+    const size_t chunk = ctx->photon_chunk;
+    const size_t first_chunk = count < chunk ? (size_t)count : chunk;
+    if (first_chunk == 0) return CGRT_OK;
+    CKS(ensure_photon_buffers(ctx, first_chunk, first_chunk * (size_t)P.max_depth));
+    std::vector<cudaEvent_t> evs;
+    const unsigned int resume_grid = ctx->deposit_grid;  // 8 resident blocks per SM, grid-stride over the queue
+    for (uint64_t done = 0; done < count; done += chunk) {
+        const size_t n = (size_t)((count - done) < chunk ? (count - done) : chunk);
+        const uint64_t base = first + done;
+        const size_t slots = n * (size_t)P.max_depth;
+        cudaEvent_t e[4] = {nullptr, nullptr, nullptr, nullptr};
+        if (ctx->profiling) {
+            for (int k = 0; k < 4; k++) { CK(cudaEventCreate(&e[k])); evs.push_back(e[k]); }
+            CK(cudaEventRecord(e[0], ctx->stream));
+        }
+        CK(cudaMemsetAsync(ctx->dep_keys, 0xff, slots * sizeof(uint32_t), ctx->stream));
+        CK(cudaMemsetAsync(ctx->dep_hist, 0, (size_t)CGRT_NBINS * sizeof(uint32_t), ctx->stream));
+        CK(cudaMemsetAsync(ctx->d_qcount + 2, 0, 6 * sizeof(unsigned int), ctx->stream));
+        unsigned int *qc = ctx->d_qcount + 2;
+#define LAUNCH_PT(F, C, GRID, QIN, NIN, QOUT, NOUT)                                                                                           \
+    photon_trace_kernel<F, C><<<GRID, CGRT_TRACE_BLOCK, 0, ctx->stream>>>(ctx->S, P, base, (unsigned int)n, QIN, NIN, QOUT, NOUT, ctx->dep_rec, \
+                                                                          ctx->dep_keys, ctx->dep_hist, ctx->d_ctr, ctx->d_tc)
+        if (ctx->counting) LAUNCH_PT(true, true, nblk(n, CGRT_TRACE_BLOCK), nullptr, nullptr, ctx->pq[0], qc);
+        else LAUNCH_PT(true, false, nblk(n, CGRT_TRACE_BLOCK), nullptr, nullptr, ctx->pq[0], qc);
+        ctx->launches++;
+        if (ctx->S.nbvh > 0) {
+            for (int pass = 1; pass <= P.max_depth; pass++) {  // a resumed photon advances at least one segment per pass
+                const PhotonState *qin = ctx->pq[(pass - 1) & 1];
+                PhotonState *qout = ctx->pq[pass & 1];
+                if (ctx->counting) LAUNCH_PT(false, true, resume_grid, qin, qc + pass - 1, qout, qc + pass);
+                else LAUNCH_PT(false, false, resume_grid, qin, qc + pass - 1, qout, qc + pass);
                 ctx->launches++;
             }
-            CK(cudaEventRecord(e2, ctx->stream));
-            CK(cudaEventSynchronize(e2));
-            CK(cudaGetLastError());
-            float t01 = 0, t12 = 0;
-            cudaEventElapsedTime(&t01, e0, e1);
-            cudaEventElapsedTime(&t12, e1, e2);
-            ctx->ms[2] += t01;
-            ctx->ms[3] += t12;
-            ctx->diffuse_hits += ndq;  // every queued deposit is one diffuse photon hit (main.cpp:101)
-            n = counts[0];
-            cur ^= 1;
         }
+#undef LAUNCH_PT
+        if (ctx->profiling) CK(cudaEventRecord(e[1], ctx->stream));
+        if (ctx->nhp > 0) {
+            const int nsb = (int)(CGRT_NBINS / (CGRT_SCAN_BLOCK * CGRT_SCAN_ITEMS));
+            bin_scan_blocks_kernel<<<nsb, CGRT_SCAN_BLOCK, 0, ctx->stream>>>(ctx->dep_hist, ctx->dep_bsum);
+            bin_scan_sums_kernel<<<1, CGRT_SCAN_BLOCK, 0, ctx->stream>>>(ctx->dep_bsum, nsb, ctx->dep_nvalid);
+            bin_scatter_kernel<<<ctx->deposit_grid, 256, 0, ctx->stream>>>(ctx->dep_keys, slots, ctx->dep_hist, ctx->dep_bsum, ctx->dep_perm);
+            ctx->launches += 3;
+            if (ctx->profiling) CK(cudaEventRecord(e[2], ctx->stream));
+            size_t spans = (slots + CGRT_DEPOSIT_SPAN - 1) / CGRT_DEPOSIT_SPAN;
+            size_t want = (spans * 32 + CGRT_DEPOSIT_BLOCK - 1) / CGRT_DEPOSIT_BLOCK;
+            unsigned int dblocks = (unsigned int)(want < (size_t)ctx->deposit_grid ? want : (size_t)ctx->deposit_grid);
+            if (ctx->cfg.accum_mode == 0)
+                photon_deposit_kernel<0><<<dblocks, CGRT_DEPOSIT_BLOCK, 0, ctx->stream>>>(P, ctx->dep_rec, ctx->dep_perm, ctx->dep_nvalid, ctx->cell_start,
+                                                                                          ctx->A.pre, ctx->A.hot, ctx->A.f, ctx->acc, ctx->d_ctr);
+            else
+                photon_deposit_kernel<1><<<dblocks, CGRT_DEPOSIT_BLOCK, 0, ctx->stream>>>(P, ctx->dep_rec, ctx->dep_perm, ctx->dep_nvalid, ctx->cell_start,
+                                                                                          ctx->A.pre, ctx->A.hot, ctx->A.f, ctx->acc, ctx->d_ctr);
+            ctx->launches++;
+        } else if (ctx->profiling) {
+            CK(cudaEventRecord(e[2], ctx->stream));
+        }
+        if (ctx->profiling) CK(cudaEventRecord(e[3], ctx->stream));
+        CK(cudaGetLastError());
     }
-    cudaEventDestroy(e0); cudaEventDestroy(e1); cudaEventDestroy(e2);
+    if (ctx->profiling) {
+        CK(cudaStreamSynchronize(ctx->stream));
+        for (size_t k = 0; k + 3 < evs.size(); k += 4) {
+            float t01 = 0, t12 = 0, t23 = 0;
+            cudaEventElapsedTime(&t01, evs[k], evs[k + 1]);
+            cudaEventElapsedTime(&t12, evs[k + 1], evs[k + 2]);
+            cudaEventElapsedTime(&t23, evs[k + 2], evs[k + 3]);
+            ctx->ms[2] += t01;
+            ctx->ms[6] += t12;
+            ctx->ms[3] += t23;
+        }
+        for (cudaEvent_t ev : evs) cudaEventDestroy(ev);
+    }
     return CGRT_OK;
 }
 
@@ -885,7 +989,7 @@ int cgrt_round_update(cgrt_ctx *ctx) {
     if (!ctx) return CGRT_ERR_INVALID;
     if (!ctx->grid_built) FAIL(CGRT_ERR_INVALID, "build the grid first");
     CK(cudaSetDevice(ctx->device));
-    PhaseTimer timer(ctx, 4);
+    PhaseTimer timer(ctx, 4, ctx->profiling != 0);  // asynchronous unless profiling
     unsigned int n = ctx->nhp;
     if (n > 0) {
         if (ctx->cfg.accum_mode == 0) round_update_kernel<0><<<nblk(n, 256), 256, 0, ctx->stream>>>(n, ctx->P.alpha, ctx->A, ctx->acc);
@@ -931,6 +1035,7 @@ int cgrt_download_hitpoints(cgrt_ctx *ctx, double *pos, double *normal, double *
     if (!ctx->grid_built) FAIL(CGRT_ERR_INVALID, "build the grid first");
     size_t m = ctx->nhp;
     if (m == 0) return CGRT_OK;
+    CK(cudaStreamSynchronize(ctx->stream));
     std::vector<HpHot> hot(m);
     std::vector<double> tmp(m * 4);
     CK(cudaMemcpy(hot.data(), ctx->A.hot, m * sizeof(HpHot), cudaMemcpyDeviceToHost));
@@ -981,6 +1086,7 @@ int cgrt_download_accum(cgrt_ctx *ctx, double *dflux, double *mcount) {
 int cgrt_download_grid(cgrt_ctx *ctx, uint32_t *cell_start) {
     if (!ctx || !cell_start) return CGRT_ERR_INVALID;
     if (!ctx->grid_built) FAIL(CGRT_ERR_INVALID, "build the grid first");
+    CK(cudaStreamSynchronize(ctx->stream));
     CK(cudaMemcpy(cell_start, ctx->cell_start, ((size_t)ctx->P.hashsize + 1) * sizeof(uint32_t), cudaMemcpyDeviceToHost));
     return CGRT_OK;
 }
@@ -993,7 +1099,7 @@ int cgrt_get_counters(cgrt_ctx *ctx, cgrt_counters *out) {
     memset(out, 0, sizeof *out);
     out->eye_segments = c.eye_segments;
     out->photon_segments = c.photon_segments;
-    out->diffuse_hits = ctx->diffuse_hits;
+    out->diffuse_hits = c.diffuse_hits;
     out->candidates = c.candidates;
     out->deposits = c.deposits;
     {
@@ -1011,6 +1117,12 @@ int cgrt_set_counting(cgrt_ctx *ctx, int on) {
     if (!ctx) return CGRT_ERR_INVALID;
     ctx->counting = on != 0;
     CK(cudaMemset(ctx->d_tc, 0, sizeof(TravCounters)));
+    return CGRT_OK;
+}
+
+int cgrt_set_profiling(cgrt_ctx *ctx, int on) {
+    if (!ctx) return CGRT_ERR_INVALID;
+    ctx->profiling = on != 0;
     return CGRT_OK;
 }
 

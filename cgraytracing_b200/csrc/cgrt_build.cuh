@@ -8,14 +8,15 @@
 namespace cgrt {
 
 // =================================================================================================================
-// Radix sort: stable LSD, 8-bit digits, 64-bit keys with a 32-bit payload (the permutation).
+// Radix sort: stable LSD, 8-bit digits, 32- or 64-bit keys with a 32-bit payload (the permutation).
 // Per pass: (1) per-tile digit histogram, (2) exclusive scan over [digit][tile], (3) stable scatter.
 // =================================================================================================================
 #define RS_THREADS 256
 #define RS_ITEMS 16
 #define RS_TILE (RS_THREADS * RS_ITEMS)
 
-__global__ void __launch_bounds__(RS_THREADS) rs_hist_kernel(const uint64_t *__restrict__ keys, int64_t n, int shift, uint32_t *__restrict__ counts, int ntiles) {
+template <typename K>
+__global__ void __launch_bounds__(RS_THREADS) rs_hist_kernel(const K *__restrict__ keys, int64_t n, int shift, uint32_t *__restrict__ counts, int ntiles) {
     __shared__ uint32_t h[256];
     h[threadIdx.x] = 0;
     __syncthreads();
@@ -65,8 +66,9 @@ __global__ void __launch_bounds__(1024) rs_scan_kernel(uint32_t *__restrict__ co
     }
 }
 
-__global__ void __launch_bounds__(RS_THREADS) rs_scatter_kernel(const uint64_t *__restrict__ keys_in, const uint32_t *__restrict__ vals_in,
-                                                                uint64_t *__restrict__ keys_out, uint32_t *__restrict__ vals_out, int64_t n, int shift,
+template <typename K>
+__global__ void __launch_bounds__(RS_THREADS) rs_scatter_kernel(const K *__restrict__ keys_in, const uint32_t *__restrict__ vals_in,
+                                                                K *__restrict__ keys_out, uint32_t *__restrict__ vals_out, int64_t n, int shift,
                                                                 const uint32_t *__restrict__ offsets, int ntiles, int first_pass) {
     __shared__ uint32_t running[256];          // per digit: global offset of this tile + keys already placed
     __shared__ uint32_t warp_cnt[RS_THREADS / 32][256];
@@ -79,7 +81,7 @@ __global__ void __launch_bounds__(RS_THREADS) rs_scatter_kernel(const uint64_t *
     for (int r = 0; r < RS_ITEMS; r++) {
         int64_t i = base + r * RS_THREADS + threadIdx.x;
         bool valid = i < n;
-        uint64_t k = valid ? keys_in[i] : 0ull;
+        K k = valid ? keys_in[i] : (K)0;
         uint32_t v = valid ? (first_pass ? (uint32_t)i : vals_in[i]) : 0u;
         uint32_t dg = valid ? ((uint32_t)(k >> shift) & 255u) : 256u;  // 256: never matches a real digit
         uint32_t mask = __match_any_sync(0xffffffffu, dg);
@@ -180,7 +182,7 @@ __global__ void lbvh_leaves_kernel(const double *__restrict__ tri9, const uint32
     tris[k] = R;
     tri_id[k] = (int)src;
     float *b = box + (size_t)(n - 1 + k) * 6;
-    const double pad = 1e-6;
+    const double pad = CGRT_BOX_PAD;  // covers the fp32 slab test's rounding (cgrt_device.cuh)
     for (int a = 0; a < 3; a++) {
         double lo = fmin(fmin(t[a], t[3 + a]), t[6 + a]), hi = fmax(fmax(t[a], t[3 + a]), t[6 + a]);
         b[a] = __double2float_rd(lo - pad - 1e-7 * fabs(lo));

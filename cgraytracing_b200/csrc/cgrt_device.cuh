@@ -52,7 +52,7 @@ __host__ __device__ __forceinline__ double max3(double a, double b, double c) {
 
 // ---------------------------------------------------------------------------------------------------------------
 // Philox4x32-10 counter RNG (replaces rand(), sampling.h). key = {seed_lo, seed_hi + pass},
-// counter = {path_lo, path_hi, dim, block}; u = (double)(word >> 1) / 2147483647.0 (the rand()/RAND_MAX lattice).
+// counter = {path_lo, path_hi, dim, block}; u = (double)(word >> 1) * 2^-31 (a 31-bit lattice like rand()/RAND_MAX).
 // ---------------------------------------------------------------------------------------------------------------
 enum { PASS_EYE = 0, PASS_PHOTON = 1, PASS_BEZIER = 2 };
 
@@ -97,30 +97,42 @@ struct Philox {
         w = idx == 2 ? buf[2] : w;
         w = idx == 3 ? buf[3] : w;
         idx++;
-        return (double)(w >> 1) / 2147483647.0;
+        return (double)(w >> 1) * (1.0 / 2147483648.0);
     }
 };
 
 #define CGRT_MAX_REJECT 64
-// sampling.h:11-20
-__host__ __device__ __forceinline__ d3 sample_sphere(Philox &g) {
-    d3 v = mk(0, 0, 0);
-    for (int it = 0; it < CGRT_MAX_REJECT; it++) {
-        double x = g.u01() * 2.0 - 1;
-        double y = g.u01() * 2.0 - 1;
-        double z = g.u01() * 2.0 - 1;
-        v = mk(x, y, z);
-        if (x * x + y * y + z * z <= 1) break;
-    }
-    return normalize(v);
+// sin and cos of 2*pi*v, v in [0,1), from +,-,* only (the library is built with -fmad=false): bit-identical on any
+// IEEE machine. Exact quadrant reduction + minimax kernels on [-pi/4, pi/4].
+__host__ __device__ __forceinline__ void sincos2pi(double v, double &s_out, double &c_out) {
+    double t = 4.0 * v;
+    int k = (int)(t + 0.5);
+    double r = t - (double)k;
+    double x = r * 1.5707963267948966;
+    double z = x * x;
+    double ps = -1.66666666666666324348e-01 + z * (8.33333333332248946124e-03 + z * (-1.98412698298579493134e-04 + z * (2.75573137070700676789e-06 +
+                z * (-2.50507602534068634195e-08 + z * 1.58969099521155010221e-10))));
+    double sn = x + x * z * ps;
+    double pc = 4.16666666666666019037e-02 + z * (-1.38888888888741095749e-03 + z * (2.48015872894767294178e-05 + z * (-2.75573143513906633035e-07 +
+                z * (2.08757232129817482790e-09 + z * -1.13596475577881948265e-11))));
+    double cs = 1.0 - 0.5 * z + z * z * pc;
+    int q = k & 3;
+    s_out = q == 0 ? sn : (q == 1 ? cs : (q == 2 ? -sn : -cs));
+    c_out = q == 0 ? cs : (q == 1 ? -sn : (q == 2 ? -cs : sn));
 }
-// sampling.h:22-29
+// sampling.h:11-20 as a distribution: uniform on the unit sphere by Archimedes' map (z = 1 - 2 u1, phi = 2 pi u2). The
+// reference rejects from the cube; two draws and no loop keep the warp converged.
+__host__ __device__ __forceinline__ d3 sample_sphere(Philox &g) {
+    double z = 1.0 - 2.0 * g.u01();
+    double sn, cs;
+    sincos2pi(g.u01(), sn, cs);
+    double r = sqrt(1.0 - z * z);
+    return mk(r * cs, r * sn, z);
+}
+// sampling.h:22-29 as a distribution: a sphere sample mirrored into the hemisphere about dir.
 __host__ __device__ __forceinline__ d3 sample_halfsphere(Philox &g, d3 dir) {
-    d3 s = mk(0, 0, 0);
-    for (int it = 0; it < CGRT_MAX_REJECT; it++) {
-        s = sample_sphere(g);
-        if (dot(s, dir) > 0) break;
-    }
+    d3 s = sample_sphere(g);
+    if (dot(s, dir) < 0) s = -s;
     return s;
 }
 // sampling.h:35-43
@@ -175,6 +187,9 @@ struct BvhDev {
     int ntris;
     int root_is_leaf;
     double orient_sign;     // winding normal * orient_sign points out of the solid
+    float root_lo[3], root_hi[3];  // padded box of the whole tree (the compaction prefilter of closest_hit_block)
+    int f32_ok;             // 1: every coordinate is within CGRT_F32_BOUND, the float slab test is conservative
+    int pad;
 };
 struct TexDev {
     const uchar4 *texels;   // row-major [H][W], texel = byte/256 (main.cpp:307-311)
@@ -212,10 +227,13 @@ struct TravCounters {
 // 0 and 1; the same decisions are taken here from signs and one comparison (exactly equivalent for finite inputs
 // whose quotients do not underflow), and the only division performed is the one that produces t.
 // ---------------------------------------------------------------------------------------------------------------
-__device__ __forceinline__ bool tri_intersect(const TriRec &T, d3 o, d3 d, double &t) {
-    d3 pa = mk(T.pa[0], T.pa[1], T.pa[2]);
-    d3 e1 = mk(T.e1[0], T.e1[1], T.e1[2]);
-    d3 e2 = mk(T.e2[0], T.e2[1], T.e2[2]);
+__device__ __forceinline__ bool tri_intersect(const TriRec *T, d3 o, d3 d, double &t) {
+    const double2 *tq = reinterpret_cast<const double2 *>(T);  // pa, e1, e2 = 9 doubles: four 16-byte loads + one 8-byte
+    double2 a0 = __ldg(tq), a1 = __ldg(tq + 1), a2 = __ldg(tq + 2), a3 = __ldg(tq + 3);
+    double a4 = __ldg(reinterpret_cast<const double *>(tq + 4));
+    d3 pa = mk(a0.x, a0.y, a1.x);
+    d3 e1 = mk(a1.y, a2.x, a2.y);
+    d3 e2 = mk(a3.x, a3.y, a4);
     d3 s = pa - o;
     double det1 = det3(d, e1, e2);
     if (det1 == 0.0 || det1 != det1) return false;  // x/0 -> inf/nan never satisfies all four tests
@@ -238,39 +256,80 @@ __device__ __forceinline__ bool tri_intersect(const TriRec &T, d3 o, d3 d, doubl
 
 // ---------------------------------------------------------------------------------------------------------------
 // BVH traversal: closest triangle with t < tmax (strict), t > 0. Stack in local memory (depth <= 64).
-// Box test: slab test in fp64 on padded float bounds with explicit fma; NaNs (0 * inf) are dropped by fmin/fmax.
+//
+// The box test never decides a hit, it only has to be conservative. Node boxes are float and padded by CGRT_BOX_PAD at
+// build time; a ray whose origin lies within CGRT_F32_BOUND of the world origin is tested in fp32 (origin and 1/dir
+// rounded to float): with |coordinates| <= 64 the rounding of the origin (<= 3.8e-6), of the subtraction (<= 7.6e-6)
+// and the relative error of 1/dir and of the product (<= 3e-7 * 128) move a slab plane by less than 5e-5 < CGRT_BOX_PAD
+// in position space, so the float interval of the padded box always contains the exact interval of the true box.
+// Rays that start farther out (photons that left through the open front of the room and came back) take the fp64 slab.
+// The triangle test itself is always the reference's fp64 arithmetic (tri_intersect).
 // ---------------------------------------------------------------------------------------------------------------
-__device__ __forceinline__ bool slab(const float *lo, const float *hi, d3 o, d3 id, double tmax, double &tnear) {
-    double tx0 = ((double)lo[0] - o.x) * id.x, tx1 = ((double)hi[0] - o.x) * id.x;
-    double ty0 = ((double)lo[1] - o.y) * id.y, ty1 = ((double)hi[1] - o.y) * id.y;
-    double tz0 = ((double)lo[2] - o.z) * id.z, tz1 = ((double)hi[2] - o.z) * id.z;
+#define CGRT_F32_BOUND 64.0
+#define CGRT_BOX_PAD 8e-5
+
+struct SlabRay {
+    float ox, oy, oz, ix, iy, iz;  // fp32 path
+    d3 o, id;                      // fp64 path
+    bool exact;
+};
+__device__ __forceinline__ SlabRay make_slab_ray(d3 o, d3 d, bool f32_ok) {
+    SlabRay r;
+    r.exact = !(f32_ok && fabs(o.x) <= CGRT_F32_BOUND && fabs(o.y) <= CGRT_F32_BOUND && fabs(o.z) <= CGRT_F32_BOUND);
+    r.o = o;
+    r.id = mk(1.0 / d.x, 1.0 / d.y, 1.0 / d.z);
+    r.ox = (float)o.x; r.oy = (float)o.y; r.oz = (float)o.z;
+    r.ix = 1.0f / (float)d.x; r.iy = 1.0f / (float)d.y; r.iz = 1.0f / (float)d.z;
+    return r;
+}
+// NaNs (0 * inf) are dropped by fmin/fmax.
+__device__ __forceinline__ bool slab64(float lx, float ly, float lz, float hx, float hy, float hz, const SlabRay &r, double tmax, float &tnear) {
+    double tx0 = ((double)lx - r.o.x) * r.id.x, tx1 = ((double)hx - r.o.x) * r.id.x;
+    double ty0 = ((double)ly - r.o.y) * r.id.y, ty1 = ((double)hy - r.o.y) * r.id.y;
+    double tz0 = ((double)lz - r.o.z) * r.id.z, tz1 = ((double)hz - r.o.z) * r.id.z;
     double tn = fmax(fmax(fmin(tx0, tx1), fmin(ty0, ty1)), fmax(fmin(tz0, tz1), 0.0));
     double tf = fmin(fmin(fmax(tx0, tx1), fmax(ty0, ty1)), fmin(fmax(tz0, tz1), tmax));
+    tnear = (float)tn;
+    return tn <= tf;
+}
+__device__ __forceinline__ bool slab32(float lx, float ly, float lz, float hx, float hy, float hz, const SlabRay &r, float tmax_up, float &tnear) {
+    float tx0 = (lx - r.ox) * r.ix, tx1 = (hx - r.ox) * r.ix;
+    float ty0 = (ly - r.oy) * r.iy, ty1 = (hy - r.oy) * r.iy;
+    float tz0 = (lz - r.oz) * r.iz, tz1 = (hz - r.oz) * r.iz;
+    float tn = fmaxf(fmaxf(fminf(tx0, tx1), fminf(ty0, ty1)), fmaxf(fminf(tz0, tz1), 0.0f));
+    float tf = fminf(fminf(fmaxf(tx0, tx1), fmaxf(ty0, ty1)), fminf(fmaxf(tz0, tz1), tmax_up));
     tnear = tn;
     return tn <= tf;
+}
+__device__ __forceinline__ bool slab_any(float lx, float ly, float lz, float hx, float hy, float hz, const SlabRay &r, double tmax, float tmax_up,
+                                         float &tnear) {
+    return r.exact ? slab64(lx, ly, lz, hx, hy, hz, r, tmax, tnear) : slab32(lx, ly, lz, hx, hy, hz, r, tmax_up, tnear);
+}
+__device__ __forceinline__ bool root_box_hit(const BvhDev &B, d3 o, d3 d, double tmax) {
+    SlabRay r = make_slab_ray(o, d, B.f32_ok != 0);
+    float tn;
+    return slab_any(B.root_lo[0], B.root_lo[1], B.root_lo[2], B.root_hi[0], B.root_hi[1], B.root_hi[2], r, tmax, __double2float_ru(tmax), tn);
 }
 
 template <bool COUNT>
 __device__ __forceinline__ bool bvh_closest(const BvhDev &B, d3 o, d3 d, double tmax, double &t_out, int &leaf_out, TravCounters *tc) {
-    d3 id = mk(1.0 / d.x, 1.0 / d.y, 1.0 / d.z);
+    SlabRay R = make_slab_ray(o, d, B.f32_ok != 0);
     double best = tmax;
+    float best_up = __double2float_ru(tmax);
     int best_leaf = -1;
     int stack[64];
     int sp = 0;
     int node = B.root_is_leaf ? ~0 : 0;
     for (;;) {
         if (node >= 0) {
-            const BvhNode *np = B.nodes + node;
             // 64 bytes as four 16-byte loads
-            const float4 *q = reinterpret_cast<const float4 *>(np);
+            const float4 *q = reinterpret_cast<const float4 *>(B.nodes + node);
             float4 q0 = __ldg(q), q1 = __ldg(q + 1), q2 = __ldg(q + 2), q3 = __ldg(q + 3);
             if (COUNT) tc->node_visits++;
-            float lo0[3] = {q0.x, q0.y, q0.z}, hi0[3] = {q0.w, q1.x, q1.y};
-            float lo1[3] = {q1.z, q1.w, q2.x}, hi1[3] = {q2.y, q2.z, q2.w};
             int c0 = __float_as_int(q3.x), c1 = __float_as_int(q3.y);
-            double tn0, tn1;
-            bool h0 = slab(lo0, hi0, o, id, best, tn0);
-            bool h1 = slab(lo1, hi1, o, id, best, tn1);
+            float tn0, tn1;
+            bool h0 = slab_any(q0.x, q0.y, q0.z, q0.w, q1.x, q1.y, R, best, best_up, tn0);
+            bool h1 = slab_any(q1.z, q1.w, q2.x, q2.y, q2.z, q2.w, R, best, best_up, tn1);
             if (h0 && h1) {
                 if (tn1 < tn0) { int tmp = c0; c0 = c1; c1 = tmp; }
                 stack[sp++] = c1;
@@ -287,8 +346,9 @@ __device__ __forceinline__ bool bvh_closest(const BvhDev &B, d3 o, d3 d, double 
             int leaf = ~node;
             if (COUNT) tc->tri_tests++;
             double t;
-            if (tri_intersect(B.tris[leaf], o, d, t) && t < best) {
+            if (tri_intersect(B.tris + leaf, o, d, t) && t < best) {
                 best = t;
+                best_up = __double2float_ru(t);
                 best_leaf = leaf;
             }
             if (sp == 0) break;
@@ -424,45 +484,50 @@ __device__ bool bezier_intersect(const BezDev &Z, d3 o, d3 d, double &len, d3 &n
 }
 
 // ---------------------------------------------------------------------------------------------------------------
-// The closest-hit loop of trace(), main.cpp:50-63: objects in insertion order, strict <, nearest starts at INF.
-// Because acceptance is `len < nearest`, a mesh may be traversed with tmax = nearest without changing the result.
+// The closest-hit loop of trace(), main.cpp:50-63: objects in insertion order, strict <, nearest starts at INF —
+// i.e. the lexicographic minimum of (len, object index) over the objects that report a hit. That formulation is
+// order-independent, which is what lets a thread block split the loop in two:
+//   phase 1  every thread evaluates the analytic primitives of its own ray (planes, spheres, Bezier) in fp64;
+//   phase 2  per BVH-backed object (mesh, displaced floor) the rays whose padded root box is reachable are compacted
+//            into a shared-memory work list with a warp ballot + one shared atomic per warp, and the FIRST `count`
+//            threads of the block traverse one listed ray each. Incoherent photon rays mostly miss the meshes, so
+//            without the compaction a warp would sit through a traversal with 2-3 live lanes (measured: 2.4).
+// A BVH candidate replaces the current nearest iff t < nearest, or t == nearest and its object precedes the holder:
+// the traversal limit is `nearest` or the next double above it accordingly, and its own test stays strict.
 // ---------------------------------------------------------------------------------------------------------------
-template <bool COUNT>
-__device__ __forceinline__ bool closest_hit(const SceneDev &S, d3 o, d3 d, Hit &h, TravCounters *tc) {
-    double nearest = CGRT_INF;
-    int id = -1, prim = -1;
-    d3 nrm = mk(0, 0, 0);
+template <int BLOCK>
+struct TraceShared {
+    double ox[BLOCK], oy[BLOCK], oz[BLOCK], dx[BLOCK], dy[BLOCK], dz[BLOCK];
+    double lim[BLOCK];            // in: traversal limit of the listed ray; out: closest t
+    int leaf[BLOCK];              // out: sorted triangle position or -1
+    unsigned short list[BLOCK];   // compacted thread slots
+    unsigned int count;
+    unsigned int scratch[8];      // per-kernel block aggregates
+};
+
+__device__ __forceinline__ double next_up(double x) { return __longlong_as_double(__double_as_longlong(x) + 1); }  // x > 0 finite
+
+// Plane part of Plane::intersect (objects.h:505-508): len, valid iff len > 0.
+__device__ __forceinline__ double plane_len(const ObjDev &O, d3 o, d3 d) {
+    d3 n = mk(O.b[0], O.b[1], O.b[2]);
+    d3 dd = mk(O.a[0], O.a[1], O.a[2]) - o;
+    return dot(dd, n) / dot(d, n);
+}
+
+struct HitAcc {
+    double nearest;
+    int id, prim;
+    d3 nrm;
+};
+
+// phase 1: analytic primitives of one ray, in object order
+__device__ __forceinline__ void analytic_phase(const SceneDev &S, d3 o, d3 d, HitAcc &A) {
+    A.nearest = CGRT_INF; A.id = -1; A.prim = -1; A.nrm = mk(0, 0, 0);
     for (int i = 0; i < S.nobj; i++) {
         const ObjDev &O = S.obj[i];
-        if (O.kind == OBJ_PLANE) {  // objects.h:505-524
-            d3 n = mk(O.b[0], O.b[1], O.b[2]);
-            d3 dd = mk(O.a[0], O.a[1], O.a[2]) - o;
-            double len = dot(dd, n) / dot(d, n);
-            if (len > 0) {
-                d3 nv = n;
-                int pr = -1;
-                if (O.bvh >= 0) {
-                    // bump height-field: accepted iff 0 < lenp < len (:514); it can only matter if it also beats nearest
-                    double lenp; int leaf;
-                    double lim = len < nearest ? len : nearest;
-                    if (bvh_closest<COUNT>(S.bvh[O.bvh], o, d, lim, lenp, leaf, tc)) {
-                        len = lenp;
-                        const TriRec &T = S.bvh[O.bvh].tris[leaf];
-                        nv = mk(T.n[0], T.n[1], T.n[2]) * S.bvh[O.bvh].orient_sign;
-                        pr = S.bvh[O.bvh].tri_id[leaf];
-                    }
-                }
-                if (len < nearest) { id = i; nearest = len; nrm = nv; prim = pr; }
-            }
-        } else if (O.kind == OBJ_MESH) {  // objects.h:405-455 -> KDTree::intersect :318-332
-            double len; int leaf;
-            const BvhDev &B = S.bvh[O.bvh];
-            if (bvh_closest<COUNT>(B, o, d, nearest, len, leaf, tc)) {
-                const TriRec &T = B.tris[leaf];
-                d3 nv = mk(T.n[0], T.n[1], T.n[2]) * B.orient_sign;
-                if (O.objtype == 2) nv = nv * ((nv.y > 0) ? 1.0 : -1.0);  // objects.h:434-436: dot with (0,1,0) is nv.y + 0 + 0
-                id = i; nearest = len; nrm = nv; prim = B.tri_id[leaf];
-            }
+        if (O.kind == OBJ_PLANE) {  // objects.h:505-524 (the displaced mesh of a bump plane is a phase-2 candidate)
+            double len = plane_len(O, o, d);
+            if (len > 0 && len < A.nearest) { A.id = i; A.nearest = len; A.nrm = mk(O.b[0], O.b[1], O.b[2]); A.prim = -1; }
         } else if (O.kind == OBJ_SPHERE) {  // objects.h:45-68
             d3 l = mk(O.a[0], O.a[1], O.a[2]) - o;
             double tca = dot(l, d);
@@ -473,25 +538,81 @@ __device__ __forceinline__ bool closest_hit(const SceneDev &S, d3 o, d3 d, Hit &
                     double thc = sqrt(O.r2 - d2);
                     double t0 = tca - thc, t1 = tca + thc;
                     double len = (t0 < 0) ? t1 : t0;
-                    if (len < nearest) {
+                    if (len < A.nearest) {
                         d3 p = o + d * len;
-                        id = i; nearest = len; prim = -1;
-                        nrm = normalize(p - mk(O.a[0], O.a[1], O.a[2]));
+                        A.id = i; A.nearest = len; A.prim = -1;
+                        A.nrm = normalize(p - mk(O.a[0], O.a[1], O.a[2]));
                     }
                 }
             }
-        } else {  // OBJ_BEZIER
+        } else if (O.kind == OBJ_BEZIER) {
             double len; d3 nv;
             if (bezier_intersect(S.bez[O.aux], o, d, len, nv)) {
-                if (len < nearest) { id = i; nearest = len; nrm = nv; prim = -1; }
+                if (len < A.nearest) { A.id = i; A.nearest = len; A.nrm = nv; A.prim = -1; }
             }
         }
     }
-    h.obj = id;
-    h.t = nearest;
-    h.n = nrm;
-    h.prim = prim;
-    return id >= 0;
+}
+// phase 2, per BVH-backed object i: does this ray have to traverse it, and up to which t (exclusive)?
+__device__ __forceinline__ bool bvh_wanted(const SceneDev &S, int i, d3 o, d3 d, const HitAcc &A, double &lim) {
+    const ObjDev &O = S.obj[i];
+    lim = (A.id > i) ? next_up(A.nearest) : A.nearest;
+    if (O.kind == OBJ_PLANE) {  // objects.h:513-517: only when the plane itself is hit, and only lenp < len
+        double len = plane_len(O, o, d);
+        if (!(len > 0)) return false;
+        lim = len < lim ? len : lim;
+    }
+    return root_box_hit(S.bvh[O.bvh], o, d, lim);
+}
+__device__ __forceinline__ void bvh_merge(const SceneDev &S, int i, int leaf, double t, HitAcc &A) {
+    const ObjDev &O = S.obj[i];
+    const BvhDev &B = S.bvh[O.bvh];
+    const TriRec &T = B.tris[leaf];
+    d3 nv = mk(T.n[0], T.n[1], T.n[2]) * B.orient_sign;
+    if (O.kind == OBJ_MESH && O.objtype == 2) nv = nv * ((nv.y > 0) ? 1.0 : -1.0);  // objects.h:434-436
+    A.id = i; A.nearest = t; A.nrm = nv; A.prim = B.tri_id[leaf];
+}
+
+// Block-cooperative form (eye pass, parity hooks): every thread of the block must call it.
+template <int BLOCK, bool COUNT>
+__device__ __forceinline__ bool closest_hit_block(const SceneDev &S, bool active, d3 o, d3 d, Hit &h, TraceShared<BLOCK> &sm, TravCounters *tc) {
+    HitAcc A;
+    A.nearest = CGRT_INF; A.id = -1; A.prim = -1; A.nrm = mk(0, 0, 0);
+    if (active) analytic_phase(S, o, d, A);
+    const int tid = threadIdx.x, lane = tid & 31;
+    for (int i = 0; i < S.nobj; i++) {  // uniform control flow: S is uniform
+        const ObjDev &O = S.obj[i];
+        if (O.bvh < 0) continue;
+        const BvhDev &B = S.bvh[O.bvh];
+        double lim = 0;
+        bool want = active && bvh_wanted(S, i, o, d, A, lim);
+        if (tid == 0) sm.count = 0;
+        __syncthreads();
+        unsigned int mask = __ballot_sync(0xffffffffu, want);
+        unsigned int base = 0;
+        if (mask) {
+            if (lane == __ffs(mask) - 1) base = atomicAdd(&sm.count, (unsigned int)__popc(mask));
+            base = __shfl_sync(0xffffffffu, base, __ffs(mask) - 1);
+        }
+        if (want) {
+            sm.list[base + __popc(mask & ((1u << lane) - 1u))] = (unsigned short)tid;
+            sm.ox[tid] = o.x; sm.oy[tid] = o.y; sm.oz[tid] = o.z;
+            sm.dx[tid] = d.x; sm.dy[tid] = d.y; sm.dz[tid] = d.z;
+            sm.lim[tid] = lim;
+        }
+        __syncthreads();
+        if (tid < (int)sm.count) {
+            int s = sm.list[tid];
+            double t; int leaf;
+            bvh_closest<COUNT>(B, mk(sm.ox[s], sm.oy[s], sm.oz[s]), mk(sm.dx[s], sm.dy[s], sm.dz[s]), sm.lim[s], t, leaf, tc);
+            sm.lim[s] = t;
+            sm.leaf[s] = leaf;
+        }
+        __syncthreads();
+        if (want && sm.leaf[tid] >= 0) bvh_merge(S, i, sm.leaf[tid], sm.lim[tid], A);
+    }
+    h.obj = A.id; h.t = A.nearest; h.n = A.nrm; h.prim = A.prim;
+    return A.id >= 0;
 }
 
 // Texture::color, texture.h:39-72; Plane::getSurfaceColor objects.h:533-539

@@ -13,16 +13,22 @@ struct RayQueue {
     uint32_t *id;    // eye: path = (h*W + w)*samples + s ; photon: offset from the call's first photon index
     uint32_t *aux;   // eye: DFS split code (nsplit << 4 | bits)
 };
-// Diffuse photon hits waiting for the 27-cell gather (main.cpp:103-125)
-struct DepositQueue {
-    double *px, *py, *pz, *nx, *ny, *nz, *fx, *fy, *fz;
-};
 
 // Hitpoint hot record read per candidate in the gather: 64 bytes (two sectors).
 struct __align__(16) HpHot {
     double px, py, pz, r2;
     double nx, ny, nz, pad;
 };
+
+// fp32 prefilter record of one hitpoint (see photon_deposit_kernel). E bounds |fl(hp) - fl(X)| - |hp - X| for any photon
+// position X within the radius: two float roundings per axis at magnitude <= m + r, sqrt(3) axes, with 2x headroom.
+__device__ __forceinline__ float4 make_prefilter(double px, double py, double pz, double r2) {
+    double r = sqrt(r2);
+    double m = fmax(fmax(fabs(px), fabs(py)), fabs(pz)) + r + 1.0;
+    double E = 4.5e-7 * m;
+    double b = (r + E) * (r + E) * (1.0 + 4e-6);
+    return make_float4((float)px, (float)py, (float)pz, __double2float_ru(b));
+}
 
 struct PassParams {
     int width, height, max_depth, samples, use_dof;
@@ -66,15 +72,19 @@ struct Counters {
 // sortkey = bucket key << 32 | (path*16 + dfs bits): sorting by it gives the reference's bucket order (hash.h:52,
 // main.cpp:252-254) whatever order the wavefront produced the hitpoints in.
 // =================================================================================================================
+#define CGRT_TRACE_BLOCK 128
+
 template <bool FIRST>
-__global__ void __launch_bounds__(128) eye_bounce_kernel(const __grid_constant__ SceneDev S, const __grid_constant__ PassParams P, int depth,
+__global__ void __launch_bounds__(CGRT_TRACE_BLOCK) eye_bounce_kernel(const __grid_constant__ SceneDev S, const __grid_constant__ PassParams P, int depth,
                                                          RayQueue qin, unsigned int n_in, int y0, RayQueue qout, unsigned int *n_out,
                                                          double *hp_rec, unsigned int *hp_count, unsigned int hp_cap, Counters *ctr) {
+    __shared__ TraceShared<CGRT_TRACE_BLOCK> sm;
     unsigned int i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= n_in) return;
-    d3 o, d, adj;
-    uint32_t path, code;
-    if (FIRST) {
+    const bool active = i < n_in;
+    d3 o = mk(0, 0, 0), d = mk(0, 0, 1), adj = mk(0, 0, 0);
+    uint32_t path = 0, code = 0;
+    if (!active) {
+    } else if (FIRST) {
         uint32_t s = i % (uint32_t)P.samples;
         uint32_t pix = i / (uint32_t)P.samples;
         int w = (int)(pix % (uint32_t)P.width), h = y0 + (int)(pix / (uint32_t)P.width);
@@ -101,10 +111,10 @@ __global__ void __launch_bounds__(128) eye_bounce_kernel(const __grid_constant__
         code = qin.aux[i];
     }
     Hit hit;
-    bool found = closest_hit<false>(S, o, d, hit, nullptr);
+    bool found = closest_hit_block<CGRT_TRACE_BLOCK, false>(S, active, o, d, hit, sm, nullptr);
     {   // segments counter: one atomic per warp
-        unsigned int act = __activemask();
-        if ((threadIdx.x & 31) == (__ffs(act) - 1)) atomicAdd(&ctr->eye_segments, (unsigned long long)__popc(act));
+        unsigned int act = __ballot_sync(0xffffffffu, active);
+        if ((threadIdx.x & 31) == 0 && act) atomicAdd(&ctr->eye_segments, (unsigned long long)__popc(act));
     }
     int mat = -1;
     d3 X = mk(0, 0, 0), n_ff = mk(0, 0, 0), n_old = mk(0, 0, 0), f = mk(0, 0, 0);
@@ -187,7 +197,8 @@ __global__ void hp_extract_keys_kernel(const double *__restrict__ rec, unsigned 
 }
 
 struct HpArrays {
-    HpHot *hot;            // pos, r2, normal
+    float4 *pre;           // fp32 prefilter {x, y, z, (r+E)^2} read per candidate
+    HpHot *hot;            // pos, r2, normal (exact test)
     double *f;             // [n][4] f*adj (+pad)
     double *flux;          // [n][4] tau (+pad)
     int *cnt;              // accepted photon count n
@@ -205,6 +216,7 @@ __global__ void hp_gather_sorted_kernel(const double *__restrict__ rec, const ui
     h.px = r[0]; h.py = r[1]; h.pz = r[2]; h.r2 = r2_init;
     h.nx = r[3]; h.ny = r[4]; h.nz = r[5]; h.pad = 0.0;
     A.hot[k] = h;
+    A.pre[k] = make_prefilter(h.px, h.py, h.pz, r2_init);
     A.f[4 * (size_t)k] = r[6]; A.f[4 * (size_t)k + 1] = r[7]; A.f[4 * (size_t)k + 2] = r[8]; A.f[4 * (size_t)k + 3] = 0.0;
     A.flux[4 * (size_t)k] = 0.0; A.flux[4 * (size_t)k + 1] = 0.0; A.flux[4 * (size_t)k + 2] = 0.0; A.flux[4 * (size_t)k + 3] = 0.0;
     A.cnt[k] = 0;
@@ -228,171 +240,321 @@ __global__ void lower_bound_table_kernel(const uint32_t *__restrict__ keys32, co
 }
 
 // =================================================================================================================
-// Photon pass: trace kernel (emission K10 fused into depth 0) + deposit kernel.
+// Photon pass (main.cpp:221-249 + the photon half of trace(), :101-128,:158-166).
+//
+// photon_trace_kernel<FIRST>: one thread owns one photon and keeps its ray in registers from bounce to bounce — there
+// are no per-bounce global ray queues for the ~96 % of segments that only meet analytic primitives. A segment whose
+// ray reaches the padded root box of a mesh (or of the displaced floor) is NOT traversed in place: the photon is
+// suspended into a compacted global queue (warp ballot + one atomic per warp) and the thread retires. The next launch
+// (<FIRST = false>) resumes exactly those photons: every lane starts with a BVH traversal, so the warp is dense where the
+// single-kernel version ran traversals with 2-5 live lanes; after that segment the photon continues analytically until
+// it needs a mesh again and is suspended into the next queue. max_depth launches bound the chain.
+// Photon k always draws Philox stream (seed, PASS_PHOTON, k, bounce): any partition of [first, first+count) over
+// launches, queues, chunks or GPUs produces the same deposits.
+//
+// Deposits go to a dense, deterministic table: slot = depth * n + k (k = photon number inside the launch), 96-byte
+// record + 32-bit bin; empty slots keep CGRT_KEY_INVALID (pre-filled by a memset). The bin histogram is accumulated by
+// the same kernel; bin_scan_* + bin_scatter_kernel then turn it into the cell-grouped order the deposit kernel walks.
 // =================================================================================================================
-template <bool FIRST, bool COUNT>
-__global__ void __launch_bounds__(128) photon_trace_kernel(const __grid_constant__ SceneDev S, const __grid_constant__ PassParams P, int depth,
-                                                           RayQueue qin, unsigned int n_in, uint64_t first_index, RayQueue qout,
-                                                           unsigned int *n_out, DepositQueue dq, unsigned int *n_dq, Counters *ctr,
-                                                           TravCounters *tcg) {
-    unsigned int i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= n_in) return;
-    d3 o, d, flux;
-    uint32_t off;
-    if (FIRST) {  // main.cpp:240-246
-        off = i;
-        Philox g;
-        g.init(P.seed, PASS_PHOTON, first_index + (uint64_t)i, 0);
-        double a = g.u01() * 4 - 2;
-        double b = g.u01() * 4 - 2;
-        d = sample_sphere(g);
-        o = mk(P.light[0], P.light[1], P.light[2]) + mk(a, 0, b);
-        flux = mk(700, 700, 700) * (CGRT_PI * 4.0);
-    } else {
-        o = mk(qin.ox[i], qin.oy[i], qin.oz[i]);
-        d = mk(qin.dx[i], qin.dy[i], qin.dz[i]);
-        flux = mk(qin.wx[i], qin.wy[i], qin.wz[i]);
-        off = qin.id[i];
-    }
-    Hit hit;
-    TravCounters tcl;
-    tcl.node_visits = 0; tcl.tri_tests = 0;
-    bool found = closest_hit<COUNT>(S, o, d, hit, &tcl);
-    if (COUNT) {
-        atomicAdd(&tcg->node_visits, tcl.node_visits);
-        atomicAdd(&tcg->tri_tests, tcl.tri_tests);
-    }
-    {
-        unsigned int act = __activemask();
-        if ((threadIdx.x & 31) == (__ffs(act) - 1)) atomicAdd(&ctr->photon_segments, (unsigned long long)__popc(act));
-    }
-    int mat = -1;
-    d3 X = mk(0, 0, 0), n_ff = mk(0, 0, 0), n_old = mk(0, 0, 0), f = mk(0, 0, 0);
-    bool into = true;
-    if (found) {
-        X = o + d * hit.t;
-        n_old = hit.n;
-        n_ff = hit.n;
-        if (dot(n_ff, d) > 0) { n_ff = -n_ff; into = false; }
-        f = surface_color(S, hit.obj, X);
-        mat = S.obj[hit.obj].material;
-    }
-    // ---- diffuse hit: queue the deposit (main.cpp:103-125 happens in photon_deposit_kernel)
-    bool dep = (mat == MAT_DIFFUSE);
-    unsigned int ds = warp_claim(dep, n_dq);
-    if (dep) {
-        dq.px[ds] = X.x; dq.py[ds] = X.y; dq.pz[ds] = X.z;
-        dq.nx[ds] = n_ff.x; dq.ny[ds] = n_ff.y; dq.nz[ds] = n_ff.z;
-        dq.fx[ds] = flux.x; dq.fy[ds] = flux.y; dq.fz[ds] = flux.z;
-    }
-    // ---- continuation
-    bool cont = found && (depth + 1 < P.max_depth);
-    d3 no = X, nd = d, nf = flux;
-    if (cont) {
-        if (mat == MAT_DIFFUSE) {  // main.cpp:126-127: uniform hemisphere, origin NOT offset, flux * f / max(f)
-            Philox g;
-            g.init(P.seed, PASS_PHOTON, first_index + (uint64_t)off, (uint32_t)depth + 1);
-            nd = sample_halfsphere(g, n_ff);
-            double p = max3(f.x, f.y, f.z);
-            nf = f * flux * (1.0 / p);
-        } else if (mat == MAT_MIRROR) {  // main.cpp:131-134
-            nd = d - n_ff * 2.0 * dot(n_ff, d);
-            no = X + n_ff * CGRT_EPS;
-            nf = f * flux * S.obj[hit.obj].refl;
-        } else {  // glass, main.cpp:140-164: 50/50 roulette, flux unchanged
-            double nc = 1.0, nt = 1.33, nnt = into ? nc / nt : nt / nc, ddn = dot(d, n_ff), cos2t;
-            d3 refl_dir = d - n_old * 2.0 * dot(n_old, d);
-            if ((cos2t = 1 - nnt * nnt * (1 - ddn * ddn)) < 0) {
-                no = X + n_ff * CGRT_EPS; nd = refl_dir;
-            } else {
-                d3 refr_dir = normalize(d * nnt - n_old * ((into ? 1 : -1) * (ddn * nnt + sqrt(cos2t))));
-                Philox g;
-                g.init(P.seed, PASS_PHOTON, first_index + (uint64_t)off, (uint32_t)depth + 1);
-                if (g.u01() < 0.5) { no = X + n_ff * CGRT_EPS; nd = refl_dir; }
-                else { no = X - n_ff * CGRT_EPS; nd = refr_dir; }
-            }
-        }
-    }
-    unsigned int s = warp_claim(cont, n_out);
-    if (cont) push_ray(qout, s, no, nd, nf, off, 0);
+#define CGRT_KEY_INVALID 0xFFFFFFFFu  /* memset pattern of an empty slot */
+#define CGRT_BIN_BITS 22               /* counting-sort bins: 4 Mi counters = 16 MB, L2-resident */
+#define CGRT_NBINS (1u << CGRT_BIN_BITS)
+
+struct __align__(32) DepositRec {
+    double pos[3], nrm[3], flux[3];  // main.cpp:103-122: intersection, face-forwarded normal, photon flux
+    int ix, iy, iz, pad0;            // hash.h:38-42 cell of pos
+    double pad1;
+};
+struct __align__(16) PhotonState {   // a suspended photon
+    double o[3], d[3], flux[3];
+    uint32_t local, depth;
+};
+
+// Bin of a deposit: any well-mixed CGRT_BIN_BITS-bit function of the cell. It only brings the records of one cell next to
+// each other (so one warp can reuse the cell's 27 candidate lists); correctness never depends on it, two cells sharing a
+// bin are told apart by their coordinates in the deposit kernel.
+__device__ __forceinline__ uint32_t cell_bin(int ix, int iy, int iz) {
+    uint32_t h = (uint32_t)ix * 0x9E3779B1u ^ (uint32_t)iy * 0x85EBCA77u ^ (uint32_t)iz * 0xC2B2AE3Du;
+    h ^= h >> 15; h *= 0x2C1B3C6Du; h ^= h >> 12;
+    return h & (CGRT_NBINS - 1u);
 }
 
-// One warp per diffuse photon hit. Lanes 0..26 look up the 3x3x3 cells (main.cpp:105-113); the candidates of all 27
-// buckets are then scanned 32 at a time (main.cpp:114-116), one 64-byte hot record per lane. Two of the 27 cells
-// hashing to the same bucket scan it twice, exactly like the reference.
-// ACC: 0 = fp64 atomics {dflux.xyz, m}; 1 = one red.global.add.v4.f32.
-template <int ACC>
-__global__ void __launch_bounds__(256) photon_deposit_kernel(const __grid_constant__ PassParams P, DepositQueue dq, unsigned int n_dq,
-                                                             const uint32_t *__restrict__ cell_start, const HpHot *__restrict__ hot,
-                                                             const double *__restrict__ hp_f, void *__restrict__ acc, Counters *ctr) {
-    const int lane = threadIdx.x & 31;
-    unsigned int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
-    unsigned int nwarps = (gridDim.x * blockDim.x) >> 5;
-    unsigned long long cand_total = 0, dep_total = 0;
-    for (unsigned int r = warp; r < n_dq; r += nwarps) {
-        d3 X = mk(dq.px[r], dq.py[r], dq.pz[r]);
-        d3 nrm = mk(dq.nx[r], dq.ny[r], dq.nz[r]);
-        d3 flux = mk(dq.fx[r], dq.fy[r], dq.fz[r]);
-        int ix, iy, iz;
-        cell_coord(X, P.celllength, ix, iy, iz);
-        ix -= 1; iy -= 1; iz -= 1;
-        uint32_t beg = 0, cnt = 0;
-        if (lane < 27) {
-            int idx = lane / 9, idy = (lane / 3) % 3, idz = lane % 3;  // idx outermost, idz innermost (main.cpp:110-112)
-            uint32_t key = cell_hash(ix + idx, iy + idy, iz + idz, P.hashsize);
-            beg = __ldg(cell_start + key);
-            cnt = __ldg(cell_start + key + 1) - beg;
+template <bool FIRST, bool COUNT>
+__global__ void __launch_bounds__(CGRT_TRACE_BLOCK) photon_trace_kernel(const __grid_constant__ SceneDev S, const __grid_constant__ PassParams P,
+                                                                        uint64_t first_index, unsigned int n, const PhotonState *__restrict__ qin,
+                                                                        const unsigned int *__restrict__ n_in, PhotonState *__restrict__ qout,
+                                                                        unsigned int *n_out, DepositRec *__restrict__ rec, uint32_t *__restrict__ keys,
+                                                                        uint32_t *__restrict__ hist, Counters *ctr, TravCounters *tcg) {
+    const unsigned int total = FIRST ? n : *n_in;
+    TravCounters tcl;
+    tcl.node_visits = 0; tcl.tri_tests = 0;
+    unsigned int nseg = 0, nhit = 0;
+    for (unsigned int i = blockIdx.x * CGRT_TRACE_BLOCK + threadIdx.x; i < total; i += gridDim.x * CGRT_TRACE_BLOCK) {
+        d3 o, d, flux;
+        unsigned int local;
+        int depth;
+        if (FIRST) {  // main.cpp:240-246
+            local = i; depth = 0;
+            Philox g;
+            g.init(P.seed, PASS_PHOTON, first_index + (uint64_t)i, 0);
+            double a = g.u01() * 4 - 2;
+            double b = g.u01() * 4 - 2;
+            d = sample_sphere(g);
+            o = mk(P.light[0], P.light[1], P.light[2]) + mk(a, 0, b);
+            flux = mk(700, 700, 700) * (CGRT_PI * 4.0);
+        } else {
+            const double2 *q = reinterpret_cast<const double2 *>(qin + i);
+            double2 q0 = __ldg(q), q1 = __ldg(q + 1), q2 = __ldg(q + 2), q3 = __ldg(q + 3), q4 = __ldg(q + 4);
+            o = mk(q0.x, q0.y, q1.x); d = mk(q1.y, q2.x, q2.y); flux = mk(q3.x, q3.y, q4.x);
+            uint64_t meta = (uint64_t)__double_as_longlong(q4.y);
+            local = (uint32_t)meta; depth = (int)(meta >> 32);
         }
-        // exclusive prefix over lanes
-        uint32_t incl = cnt;
-#pragma unroll
-        for (int o = 1; o < 32; o <<= 1) {
-            uint32_t y = __shfl_up_sync(0xffffffffu, incl, o);
-            if (lane >= o) incl += y;
-        }
-        uint32_t excl = incl - cnt;
-        uint32_t total = __shfl_sync(0xffffffffu, incl, 31);
-        cand_total += (lane == 0) ? total : 0;
-        for (uint32_t c0 = 0; c0 < total; c0 += 32) {
-            uint32_t c = c0 + lane;
-            // find the cell whose [excl, excl+cnt) contains c: count lanes with excl <= c, via a ballot-free binary search
-            int lo = 0;
-#pragma unroll
-            for (int step = 16; step >= 1; step >>= 1) {
-                int probe = lo + step;
-                uint32_t e = __shfl_sync(0xffffffffu, excl, probe & 31);
-                if (probe < 27 && e <= c) lo = probe;
+        const uint64_t index = first_index + (uint64_t)local;
+        bool resume = !FIRST;  // the segment a suspended photon was waiting for: traverse here
+        for (; depth < P.max_depth; depth++) {
+            HitAcc A;
+            analytic_phase(S, o, d, A);
+            bool suspended = false;
+            for (int k = 0; k < S.nobj; k++) {
+                if (S.obj[k].bvh < 0) continue;
+                double lim;
+                if (!bvh_wanted(S, k, o, d, A, lim)) continue;
+                if (FIRST || !resume) { suspended = true; break; }
+                double t; int leaf;
+                if (bvh_closest<COUNT>(S.bvh[S.obj[k].bvh], o, d, lim, t, leaf, &tcl)) bvh_merge(S, k, leaf, t, A);
             }
-            // lo may point at an empty cell that shares excl with later ones; the last lane with excl <= c is the owner
-            uint32_t e_lo = __shfl_sync(0xffffffffu, excl, lo);
-            uint32_t b_lo = __shfl_sync(0xffffffffu, beg, lo);
-            if (c < total) {
-                uint32_t hidx = b_lo + (c - e_lo);
-                const double2 *hp = reinterpret_cast<const double2 *>(hot + hidx);
-                double2 a0 = __ldg(hp), a1 = __ldg(hp + 1), b0 = __ldg(hp + 2), b1 = __ldg(hp + 3);
-                d3 hpos = mk(a0.x, a0.y, a1.x);
-                double r2 = a1.y;
-                d3 hn = mk(b0.x, b0.y, b1.x);
-                d3 dd = hpos - X;
-                if ((dot(hn, nrm) > CGRT_EPS) && (dot(dd, dd) <= r2)) {  // main.cpp:116
-                    const double2 *fp = reinterpret_cast<const double2 *>(hp_f + 4 * (size_t)hidx);
-                    double2 f0 = __ldg(fp), f1 = __ldg(fp + 1);
-                    d3 cc = (mk(f0.x, f0.y, f1.x) * flux) * (1.0 / CGRT_PI);  // f.mul(flux) * (1/PI), main.cpp:122
-                    if (ACC == 0) {
-                        double *ap = reinterpret_cast<double *>(acc) + 4 * (size_t)hidx;
-                        atomicAdd(ap, cc.x); atomicAdd(ap + 1, cc.y); atomicAdd(ap + 2, cc.z); atomicAdd(ap + 3, 1.0);
-                    } else {
-                        float *ap = reinterpret_cast<float *>(acc) + 4 * (size_t)hidx;
-                        asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(ap), "f"((float)cc.x), "f"((float)cc.y),
-                                     "f"((float)cc.z), "f"(1.0f)
-                                     : "memory");
-                    }
-                    dep_total++;
+            {   // suspend: compact into the next queue
+                unsigned int act = __activemask();
+                unsigned int m = __ballot_sync(act, suspended);
+                if (suspended) {
+                    int lane = threadIdx.x & 31, leader = __ffs(m) - 1;
+                    unsigned int base = 0;
+                    if (lane == leader) base = atomicAdd(n_out, (unsigned int)__popc(m));
+                    base = __shfl_sync(m, base, leader);
+                    double2 *q = reinterpret_cast<double2 *>(qout + base + __popc(m & ((1u << lane) - 1u)));
+                    uint64_t meta = ((uint64_t)(uint32_t)depth << 32) | (uint64_t)local;
+                    q[0] = make_double2(o.x, o.y); q[1] = make_double2(o.z, d.x); q[2] = make_double2(d.y, d.z);
+                    q[3] = make_double2(flux.x, flux.y); q[4] = make_double2(flux.z, __longlong_as_double((long long)meta));
+                }
+            }
+            if (suspended) break;
+            resume = false;
+            nseg++;
+            if (A.id < 0) break;  // main.cpp:64-66
+            d3 X = o + d * A.nearest;  // main.cpp:68
+            d3 n_old = A.nrm, n_ff = A.nrm;
+            bool into = true;
+            if (dot(n_ff, d) > 0) { n_ff = -n_ff; into = false; }  // main.cpp:73-76
+            d3 f = surface_color(S, A.id, X);
+            const int mat = S.obj[A.id].material;
+            if (mat == MAT_DIFFUSE) {  // the 27-cell gather of main.cpp:103-125 runs in photon_deposit_kernel
+                const size_t slot = (size_t)depth * (size_t)n + (size_t)local;
+                int ix, iy, iz;
+                cell_coord(X, P.celllength, ix, iy, iz);
+                double4 *r = reinterpret_cast<double4 *>(rec + slot);
+                r[0] = make_double4(X.x, X.y, X.z, n_ff.x);
+                r[1] = make_double4(n_ff.y, n_ff.z, flux.x, flux.y);
+                int4 c = make_int4(ix, iy, iz, 0);
+                r[2] = make_double4(flux.z, __longlong_as_double(((long long)(uint32_t)c.y << 32) | (uint32_t)c.x),
+                                    __longlong_as_double((long long)(uint32_t)c.z), 0.0);
+                const uint32_t bin = cell_bin(ix, iy, iz);
+                keys[slot] = bin;
+                atomicAdd(hist + bin, 1u);  // histogram of the counting sort, fused into the producer
+                nhit++;
+            }
+            if (depth + 1 >= P.max_depth) break;
+            if (mat == MAT_DIFFUSE) {  // main.cpp:126-127: uniform hemisphere, origin NOT offset, flux * f / max(f)
+                Philox g;
+                g.init(P.seed, PASS_PHOTON, index, (uint32_t)depth + 1);
+                d = sample_halfsphere(g, n_ff);
+                double p = max3(f.x, f.y, f.z);
+                flux = f * flux * (1.0 / p);
+                o = X;
+            } else if (mat == MAT_MIRROR) {  // main.cpp:131-134
+                d = d - n_ff * 2.0 * dot(n_ff, d);
+                o = X + n_ff * CGRT_EPS;
+                flux = f * flux * S.obj[A.id].refl;
+            } else {  // glass, main.cpp:140-164: 50/50 roulette, flux unchanged
+                double nc = 1.0, nt = 1.33, nnt = into ? nc / nt : nt / nc, ddn = dot(d, n_ff), cos2t;
+                d3 refl_dir = d - n_old * 2.0 * dot(n_old, d);
+                if ((cos2t = 1 - nnt * nnt * (1 - ddn * ddn)) < 0) {
+                    o = X + n_ff * CGRT_EPS; d = refl_dir;
+                } else {
+                    d3 refr_dir = normalize(d * nnt - n_old * ((into ? 1 : -1) * (ddn * nnt + sqrt(cos2t))));
+                    Philox g;
+                    g.init(P.seed, PASS_PHOTON, index, (uint32_t)depth + 1);
+                    if (g.u01() < 0.5) { o = X + n_ff * CGRT_EPS; d = refl_dir; }
+                    else { o = X - n_ff * CGRT_EPS; d = refr_dir; }
                 }
             }
         }
     }
+    // ---- counters: warp reduce, one atomic per warp and counter
+    unsigned int nn = COUNT ? (unsigned int)tcl.node_visits : 0u, nt_ = COUNT ? (unsigned int)tcl.tri_tests : 0u;
+#pragma unroll
+    for (int off = 16; off > 0; off >>= 1) {
+        nseg += __shfl_xor_sync(0xffffffffu, nseg, off);
+        nhit += __shfl_xor_sync(0xffffffffu, nhit, off);
+        if (COUNT) { nn += __shfl_xor_sync(0xffffffffu, nn, off); nt_ += __shfl_xor_sync(0xffffffffu, nt_, off); }
+    }
+    if ((threadIdx.x & 31) == 0) {
+        if (nseg) atomicAdd(&ctr->photon_segments, (unsigned long long)nseg);
+        if (nhit) atomicAdd(&ctr->diffuse_hits, (unsigned long long)nhit);
+        if (COUNT) {
+            if (nn) atomicAdd(&tcg->node_visits, (unsigned long long)nn);
+            if (nt_) atomicAdd(&tcg->tri_tests, (unsigned long long)nt_);
+        }
+    }
+}
+
+// ---------------------------------------------------------------------------------------------------------------------
+// photon_deposit_kernel: the 27-cell gather and deposit of main.cpp:103-125 over deposit records SORTED by cell.
+//
+// One warp owns a contiguous range of the sorted order. Per batch of 32 records it forms groups of records that lie in
+// the same cell; a group shares its candidate list (the hitpoints of the 3x3x3 buckets, read once per group instead of
+// once per photon hit): lanes hold 32 candidates at a time, the group's hit positions are broadcast by shuffle, and every
+// (hit, candidate) pair first passes a 16-byte fp32 prefilter {x, y, z, (r + E)^2} (E bounds the float rounding of both
+// positions: the filter can only pass too much). Surviving pairs (~10-15 %) are compacted into a per-warp shared-memory
+// queue and processed 32 at a time by ALL lanes with the reference's exact fp64 test (main.cpp:116) on the 64-byte exact
+// records, then deposited with atomics. Two of the 27 cells hashing to one bucket list it twice, like the reference
+// (SURVEY Q13). ACC: 0 = fp64 atomics {dflux.xyz, m}; 1 = one red.global.add.v4.f32.
+// ---------------------------------------------------------------------------------------------------------------------
+#define CGRT_DEPOSIT_BLOCK 256
+#define CGRT_DEPOSIT_SPAN 128   /* sorted records per warp */
+
+__device__ __forceinline__ double4 ldg4(const double4 *p) {  // 32 bytes as two 16-byte read-only loads
+    const double2 *q = reinterpret_cast<const double2 *>(p);
+    double2 a = __ldg(q), b = __ldg(q + 1);
+    return make_double4(a.x, a.y, b.x, b.y);
+}
+
+template <int ACC>
+__device__ __forceinline__ void deposit_exact(const DepositRec *__restrict__ rec, uint32_t src, uint32_t hidx, const HpHot *__restrict__ hot,
+                                              const double *__restrict__ hp_f, void *__restrict__ acc, unsigned int &ndep) {
+    const double4 *r = reinterpret_cast<const double4 *>(rec + src);
+    double4 r0 = ldg4(r), r1 = ldg4(r + 1);
+    double fz = __ldg(reinterpret_cast<const double *>(r + 2));
+    const double2 *hp = reinterpret_cast<const double2 *>(hot + hidx);
+    double2 a0 = __ldg(hp), a1 = __ldg(hp + 1), b0 = __ldg(hp + 2), b1 = __ldg(hp + 3);
+    d3 X = mk(r0.x, r0.y, r0.z), nrm = mk(r0.w, r1.x, r1.y), flux = mk(r1.z, r1.w, fz);
+    d3 hpos = mk(a0.x, a0.y, a1.x);
+    double r2 = a1.y;
+    d3 hn = mk(b0.x, b0.y, b1.x);
+    d3 dd = hpos - X;
+    if ((dot(hn, nrm) > CGRT_EPS) && (dot(dd, dd) <= r2)) {  // main.cpp:116
+        const double2 *fp = reinterpret_cast<const double2 *>(hp_f + 4 * (size_t)hidx);
+        double2 f0 = __ldg(fp), f1 = __ldg(fp + 1);
+        d3 cc = (mk(f0.x, f0.y, f1.x) * flux) * (1.0 / CGRT_PI);  // f.mul(flux) * (1/PI), main.cpp:122
+        if (ACC == 0) {
+            double *ap = reinterpret_cast<double *>(acc) + 4 * (size_t)hidx;
+            atomicAdd(ap, cc.x); atomicAdd(ap + 1, cc.y); atomicAdd(ap + 2, cc.z); atomicAdd(ap + 3, 1.0);
+        } else {
+            float *ap = reinterpret_cast<float *>(acc) + 4 * (size_t)hidx;
+            asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(ap), "f"((float)cc.x), "f"((float)cc.y), "f"((float)cc.z), "f"(1.0f)
+                         : "memory");
+        }
+        ndep++;
+    }
+}
+
+template <int ACC>
+__global__ void __launch_bounds__(CGRT_DEPOSIT_BLOCK) photon_deposit_kernel(const __grid_constant__ PassParams P, const DepositRec *__restrict__ rec,
+                                                                            const uint32_t *__restrict__ perm, const uint32_t *__restrict__ n_valid,
+                                                                            const uint32_t *__restrict__ cell_start,
+                                                                            const float4 *__restrict__ pre, const HpHot *__restrict__ hot,
+                                                                            const double *__restrict__ hp_f, void *__restrict__ acc, Counters *ctr) {
+    __shared__ uint2 queue_all[CGRT_DEPOSIT_BLOCK / 32][64];
+    const int lane = threadIdx.x & 31;
+    uint2 *queue = queue_all[threadIdx.x >> 5];
+    const unsigned int lt = (1u << lane) - 1u;
+    const size_t warp = ((size_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const size_t nwarps = ((size_t)gridDim.x * blockDim.x) >> 5;
+    unsigned long long cand_total = 0;
+    unsigned int ndep = 0;
+    const int idx = lane / 9, idy = (lane / 3) % 3, idz = lane % 3;  // idx outermost, idz innermost (main.cpp:110-112)
+    int qn = 0;
+    const size_t n_slots = (size_t)__ldg(n_valid);
+    for (size_t span = warp * CGRT_DEPOSIT_SPAN; span < n_slots; span += nwarps * CGRT_DEPOSIT_SPAN) {
+        const size_t span_end = span + CGRT_DEPOSIT_SPAN < n_slots ? span + CGRT_DEPOSIT_SPAN : n_slots;
+        for (size_t base = span; base < span_end; base += 32) {
+            const size_t j = base + lane;
+            bool valid = j < span_end;
+            uint32_t src = 0;
+            float xf = 0, yf = 0, zf = 0;
+            int ix = 0, iy = 0, iz = 0;
+            if (valid) {
+                src = __ldg(perm + j);
+                const double4 *r = reinterpret_cast<const double4 *>(rec + src);
+                double4 r0 = ldg4(r), r2 = ldg4(r + 2);
+                xf = (float)r0.x; yf = (float)r0.y; zf = (float)r0.z;
+                long long cxy = __double_as_longlong(r2.y);
+                ix = (int)(uint32_t)cxy; iy = (int)(uint32_t)(cxy >> 32); iz = (int)(uint32_t)__double_as_longlong(r2.z);
+            }
+            unsigned int remaining = __ballot_sync(0xffffffffu, valid);
+            while (remaining) {
+                const int leader = __ffs(remaining) - 1;
+                const int cx = __shfl_sync(0xffffffffu, ix, leader), cy = __shfl_sync(0xffffffffu, iy, leader), cz = __shfl_sync(0xffffffffu, iz, leader);
+                const unsigned int grp = __ballot_sync(0xffffffffu, valid && ix == cx && iy == cy && iz == cz) & remaining;
+                remaining &= ~grp;
+                // the 27 bucket ranges of this cell (main.cpp:105-113)
+                uint32_t beg = 0, cnt = 0;
+                if (lane < 27) {
+                    uint32_t key = cell_hash(cx - 1 + idx, cy - 1 + idy, cz - 1 + idz, P.hashsize);
+                    beg = __ldg(cell_start + key);
+                    cnt = __ldg(cell_start + key + 1) - beg;
+                }
+                uint32_t incl = cnt;
+#pragma unroll
+                for (int o = 1; o < 32; o <<= 1) {
+                    uint32_t y = __shfl_up_sync(0xffffffffu, incl, o);
+                    if (lane >= o) incl += y;
+                }
+                const uint32_t excl = incl - cnt;
+                const uint32_t total = __shfl_sync(0xffffffffu, incl, 31);
+                cand_total += (lane == 0) ? (unsigned long long)total * (unsigned int)__popc(grp) : 0ull;
+                for (uint32_t c0 = 0; c0 < total; c0 += 32) {
+                    const uint32_t c = c0 + lane;
+                    // owner cell of candidate c = last lane < 27 whose excl <= c (shuffle binary search)
+                    int lo = 0;
+#pragma unroll
+                    for (int step = 16; step >= 1; step >>= 1) {
+                        int probe = lo + step;
+                        uint32_t e = __shfl_sync(0xffffffffu, excl, probe & 31);
+                        if (probe < 27 && e <= c) lo = probe;
+                    }
+                    const uint32_t e_lo = __shfl_sync(0xffffffffu, excl, lo);
+                    const uint32_t b_lo = __shfl_sync(0xffffffffu, beg, lo);
+                    const bool have = c < total;
+                    const uint32_t hidx = have ? b_lo + (c - e_lo) : 0u;
+                    float4 q = have ? __ldg(pre + hidx) : make_float4(0.f, 0.f, 0.f, -1.f);
+                    for (unsigned int m = grp; m; m &= m - 1) {
+                        const int hl = __ffs(m) - 1;
+                        const float hx = __shfl_sync(0xffffffffu, xf, hl), hy = __shfl_sync(0xffffffffu, yf, hl), hz = __shfl_sync(0xffffffffu, zf, hl);
+                        const uint32_t hsrc = __shfl_sync(0xffffffffu, src, hl);
+                        const float ddx = q.x - hx, ddy = q.y - hy, ddz = q.z - hz;
+                        const bool pass = ddx * ddx + ddy * ddy + ddz * ddz <= q.w;
+                        const unsigned int pm = __ballot_sync(0xffffffffu, pass);
+                        if (pass) queue[qn + __popc(pm & lt)] = make_uint2(hsrc, hidx);
+                        qn += __popc(pm);
+                        if (qn >= 32) {
+                            __syncwarp();
+                            uint2 pr = queue[qn - 32 + lane];
+                            qn -= 32;
+                            deposit_exact<ACC>(rec, pr.x, pr.y, hot, hp_f, acc, ndep);
+                            __syncwarp();
+                        }
+                    }
+                }
+            }
+        }
+    }
+    __syncwarp();
+    if (lane < qn) {
+        uint2 pr = queue[lane];
+        deposit_exact<ACC>(rec, pr.x, pr.y, hot, hp_f, acc, ndep);
+    }
     // counters: warp-reduce then one atomic per warp
+    unsigned long long dep_total = ndep;
     for (int o = 16; o > 0; o >>= 1) {
         cand_total += __shfl_xor_sync(0xffffffffu, cand_total, o);
         dep_total += __shfl_xor_sync(0xffffffffu, dep_total, o);
@@ -400,6 +562,67 @@ __global__ void __launch_bounds__(256) photon_deposit_kernel(const __grid_consta
     if (lane == 0) {
         if (cand_total) atomicAdd(&ctr->candidates, cand_total);
         if (dep_total) atomicAdd(&ctr->deposits, dep_total);
+    }
+}
+
+// ---------------------------------------------------------------------------------------------------------------------
+// Counting sort of the deposit slots by bin (not stable: the order inside a bin is irrelevant). The histogram comes from
+// photon_trace_kernel; three small kernels scan it exclusively in place, and the scatter turns every valid slot into one
+// entry of `perm` with a returning atomic on its bin cursor.
+// ---------------------------------------------------------------------------------------------------------------------
+#define CGRT_SCAN_BLOCK 1024
+#define CGRT_SCAN_ITEMS 4
+
+__device__ __forceinline__ uint32_t block_exclusive_scan_1024(uint32_t v, uint32_t *warp_sums, uint32_t &block_total) {
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+    uint32_t x = v;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        uint32_t y = __shfl_up_sync(0xffffffffu, x, o);
+        if (lane >= o) x += y;
+    }
+    if (lane == 31) warp_sums[wid] = x;
+    __syncthreads();
+    if (wid == 0) {
+        uint32_t s = warp_sums[lane];
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            uint32_t y = __shfl_up_sync(0xffffffffu, s, o);
+            if (lane >= o) s += y;
+        }
+        warp_sums[lane] = s;
+    }
+    __syncthreads();
+    block_total = warp_sums[31];
+    return (wid > 0 ? warp_sums[wid - 1] : 0u) + x - v;
+}
+// phase 1: per block of 4096 counters, exclusive scan in place + block total
+__global__ void __launch_bounds__(CGRT_SCAN_BLOCK) bin_scan_blocks_kernel(uint32_t *__restrict__ hist, uint32_t *__restrict__ block_sums) {
+    __shared__ uint32_t ws[32];
+    uint4 *p = reinterpret_cast<uint4 *>(hist) + (size_t)blockIdx.x * CGRT_SCAN_BLOCK + threadIdx.x;
+    uint4 v = *p;
+    uint32_t total;
+    uint32_t ex = block_exclusive_scan_1024(v.x + v.y + v.z + v.w, ws, total);
+    *p = make_uint4(ex, ex + v.x, ex + v.x + v.y, ex + v.x + v.y + v.z);
+    if (threadIdx.x == 0) block_sums[blockIdx.x] = total;
+}
+// phase 2: one block scans the (<= 1024) block totals; the grand total is the number of valid deposit slots
+__global__ void __launch_bounds__(CGRT_SCAN_BLOCK) bin_scan_sums_kernel(uint32_t *__restrict__ block_sums, int nblocks, uint32_t *__restrict__ n_valid) {
+    __shared__ uint32_t ws[32];
+    uint32_t v = (int)threadIdx.x < nblocks ? block_sums[threadIdx.x] : 0u;
+    uint32_t total;
+    uint32_t ex = block_exclusive_scan_1024(v, ws, total);
+    if ((int)threadIdx.x < nblocks) block_sums[threadIdx.x] = ex;
+    if (threadIdx.x == 0) *n_valid = total;
+}
+// phase 3 fused into the scatter: cursor of bin b = hist[b] + block_sums[b / 4096]
+__global__ void __launch_bounds__(256) bin_scatter_kernel(const uint32_t *__restrict__ keys, size_t n_slots, uint32_t *__restrict__ hist,
+                                                          const uint32_t *__restrict__ block_sums, uint32_t *__restrict__ perm) {
+    for (size_t s = (size_t)blockIdx.x * blockDim.x + threadIdx.x; s < n_slots; s += (size_t)gridDim.x * blockDim.x) {
+        uint32_t b = __ldg(keys + s);
+        if (b == CGRT_KEY_INVALID) continue;
+        uint32_t pos = atomicAdd(hist + b, 1u) + __ldg(block_sums + (b >> 12));
+        perm[pos] = (uint32_t)s;
     }
 }
 
@@ -431,7 +654,10 @@ __global__ void round_update_kernel(unsigned int n, double alpha, HpArrays A, vo
         fl[0] = (fl[0] + dx) * g;
         fl[1] = (fl[1] + dy) * g;
         fl[2] = (fl[2] + dz) * g;
-        A.hot[k].r2 *= g;
+        HpHot hh = A.hot[k];
+        hh.r2 *= g;
+        A.hot[k].r2 = hh.r2;
+        A.pre[k] = make_prefilter(hh.px, hh.py, hh.pz, hh.r2);
         A.cnt[k] = cnt + (int)m;
     }
 }
@@ -468,20 +694,23 @@ __global__ void image_gather_kernel(int width, int height, double n_emitted, con
 // Parity-hook kernels
 // =================================================================================================================
 template <bool COUNT>
-__global__ void __launch_bounds__(128) intersect_batch_kernel(const __grid_constant__ SceneDev S, int64_t n, const double *__restrict__ org,
-                                                              const double *__restrict__ dir, double *t, double *nrm, double *nrm_raw, int *obj,
-                                                              int *into, int *prim, TravCounters *tc_out) {
+__global__ void __launch_bounds__(CGRT_TRACE_BLOCK) intersect_batch_kernel(const __grid_constant__ SceneDev S, int64_t n, const double *__restrict__ org,
+                                                                           const double *__restrict__ dir, double *t, double *nrm, double *nrm_raw,
+                                                                           int *obj, int *into, int *prim, TravCounters *tc_out) {
+    __shared__ TraceShared<CGRT_TRACE_BLOCK> sm;
     int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= n) return;
-    d3 o = mk(org[3 * i], org[3 * i + 1], org[3 * i + 2]), d = mk(dir[3 * i], dir[3 * i + 1], dir[3 * i + 2]);
+    const bool active = i < n;
+    d3 o = mk(0, 0, 0), d = mk(0, 0, 1);
+    if (active) { o = mk(org[3 * i], org[3 * i + 1], org[3 * i + 2]); d = mk(dir[3 * i], dir[3 * i + 1], dir[3 * i + 2]); }
     Hit h;
     TravCounters tc;
     tc.node_visits = 0; tc.tri_tests = 0;
-    bool found = closest_hit<COUNT>(S, o, d, h, &tc);
+    bool found = closest_hit_block<CGRT_TRACE_BLOCK, COUNT>(S, active, o, d, h, sm, &tc);
     if (COUNT) {
         atomicAdd(&tc_out->node_visits, tc.node_visits);
         atomicAdd(&tc_out->tri_tests, tc.tri_tests);
     }
+    if (!active) return;
     d3 nf = h.n;
     int in = 1;
     if (found && dot(nf, d) > 0) { nf = -nf; in = 0; }

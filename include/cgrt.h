@@ -141,8 +141,11 @@ int cgrt_get_counters(cgrt_ctx *ctx, cgrt_counters *out);
 /* on != 0: the photon trace kernels run their counting build (same traversal + node-visit / triangle-test counters,
  * reported by cgrt_get_counters). Used outside timed regions to derive the algorithmic bytes of the roofline. */
 int cgrt_set_counting(cgrt_ctx *ctx, int on);
+/* on != 0: every photon kernel launch is bracketed by CUDA events on the ctx stream and cgrt_photon_pass ends with a
+ * synchronise (per-kernel durations for the roofline). Off (default): cgrt_photon_pass is asynchronous. */
+int cgrt_set_profiling(cgrt_ctx *ctx, int on);
 /* Accumulated device time per phase on the ctx stream (CUDA events), milliseconds: [0] eye, [1] grid, [2] photon trace kernels,
- * [3] photon deposit kernels, [4] update, [5] gather. */
+ * [3] photon deposit kernel, [6] deposit-key radix sort ([2],[3],[6] only while profiling is on), [4] update, [5] gather. */
 int cgrt_get_timings(cgrt_ctx *ctx, double ms[8]);
 
 #ifdef __cplusplus

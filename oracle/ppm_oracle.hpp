@@ -103,8 +103,8 @@ inline int gammaCorr(double x) { return int(std::pow(1 - std::exp(-x), 1 / 2.2) 
 //     call order (used to pin the oracle bit-for-bit against oracle/_ref, whose rand() is interposed
 //     with the same sequence);
 //   * Philox4x32-10 counter streams (the definition shared with the GPU): key = {seed_lo, seed_hi + pass},
-//     counter = {path_lo, path_hi, dim, block}; word w -> u = (double)(w >> 1) / 2147483647.0, i.e. the
-//     same 31-bit lattice on [0,1] as rand()/RAND_MAX.
+//     counter = {path_lo, path_hi, dim, block}; word w -> u = (double)(w >> 1) * 2^-31, a 31-bit lattice on
+//     [0,1) like rand()/RAND_MAX's on [0,1] (one exact multiply instead of an fp64 division on the GPU).
 // ------------------------------------------------------------------------------------------------
 inline void philox4x32_10(const uint32_t ctr_in[4], const uint32_t key_in[2], uint32_t out[4]) {
     uint32_t c0 = ctr_in[0], c1 = ctr_in[1], c2 = ctr_in[2], c3 = ctr_in[3];
@@ -159,15 +159,48 @@ struct Rng {
             ctr[3]++;
             idx = 0;
         }
-        return (double)(buf[idx++] >> 1) / 2147483647.0;
+        return (double)(buf[idx++] >> 1) * (1.0 / 2147483648.0);
     }
 };
 
 // Rejection loops are bounded so the GPU twin cannot spin forever; P(64 consecutive rejections) < 1e-20.
 static const int MAX_REJECT = 64;
 
-// sampling.h:11-20
+// sin and cos of 2*pi*v for v in [0,1), from +,-,* only (no libm, no contraction), so that the CPU oracle and the GPU
+// produce identical bits. Quadrant reduction is exact (4v, k = round-to-nearest quadrant, 4v - k are exact in binary
+// fp64); the kernels are the classical minimax polynomials on [-pi/4, pi/4] (error < 1e-16).
+inline void sincos2pi(double v, double &s_out, double &c_out) {
+    double t = 4.0 * v;
+    int k = (int)(t + 0.5);
+    double r = t - (double)k;
+    double x = r * 1.5707963267948966;
+    double z = x * x;
+    double ps = -1.66666666666666324348e-01 + z * (8.33333333332248946124e-03 + z * (-1.98412698298579493134e-04 + z * (2.75573137070700676789e-06 +
+                z * (-2.50507602534068634195e-08 + z * 1.58969099521155010221e-10))));
+    double sn = x + x * z * ps;
+    double pc = 4.16666666666666019037e-02 + z * (-1.38888888888741095749e-03 + z * (2.48015872894767294178e-05 + z * (-2.75573143513906633035e-07 +
+                z * (2.08757232129817482790e-09 + z * -1.13596475577881948265e-11))));
+    double cs = 1.0 - 0.5 * z + z * z * pc;
+    switch (k & 3) {
+        case 0: s_out = sn; c_out = cs; break;
+        case 1: s_out = cs; c_out = -sn; break;
+        case 2: s_out = -sn; c_out = -cs; break;
+        default: s_out = -cs; c_out = sn; break;
+    }
+}
+
+// sampling.h:11-20. libc mode: the reference's rejection loop draw for draw (pins the oracle to the compiled reference).
+// Philox mode (the definition shared with the GPU): the same uniform distribution on the sphere by Archimedes' map,
+// z = 1 - 2 u1, phi = 2 pi u2 — two draws, no rejection, hence no divergent loop on the GPU (any exact sampler
+// of the same distribution is admissible; tests/test_oracle_golden.py checks the two samplers agree in distribution).
 inline Vec3 uniform_sampling_sphere(Rng &rng) {
+    if (rng.mode != 0) {
+        double z = 1.0 - 2.0 * rng.u01();
+        double sn, cs;
+        sincos2pi(rng.u01(), sn, cs);
+        double r = std::sqrt(1.0 - z * z);
+        return Vec3(r * cs, r * sn, z);
+    }
     Vec3 v;
     for (int it = 0; it < MAX_REJECT; it++) {
         double x = rng.u01() * 2.0 - 1;
@@ -178,8 +211,13 @@ inline Vec3 uniform_sampling_sphere(Rng &rng) {
     }
     return v.normalize();
 }
-// sampling.h:22-29
+// sampling.h:22-29. Philox mode: a uniform sphere sample mirrored into the hemisphere (measure preserving).
 inline Vec3 uniform_sampling_halfsphere(Rng &rng, const Vec3 &dir) {
+    if (rng.mode != 0) {
+        Vec3 s = uniform_sampling_sphere(rng);
+        if (s.dot(dir) < 0) s = Vec3(-s.x, -s.y, -s.z);
+        return s;
+    }
     Vec3 s;
     for (int it = 0; it < MAX_REJECT; it++) {
         s = uniform_sampling_sphere(rng);
