@@ -241,21 +241,23 @@ def run_gpu(args):
     t_trace = (tp1["photon_trace"] - tp0["photon_trace"]) * 1e-3
     t_dep = (tp1["photon_deposit"] - tp0["photon_deposit"]) * 1e-3
     t_upd = (tp1["update"] - tp0["update"]) * 1e-3
-    n_launch = (P + (4 << 20) - 1) // (4 << 20)
+    n_launch = (P + (16 << 20) - 1) // (16 << 20)  # chunks per round (cgrt_ctx::photon_chunk)
+    t_sort = (tp1["deposit_sort"] - tp0["deposit_sort"]) * 1e-3
     bytes_trace = seg * (B_SEGMENT + B_NODE * per_seg_nodes + B_TRI * per_seg_tris)
     bytes_dep = hits * B_CELLS + cand * B_CAND + dep * B_DEP
     kernels = {
-        "photon_trace_kernel": {"seconds": t_trace, "alg_bytes": bytes_trace, "gbps": bytes_trace / t_trace / 1e9, "launches": n_launch,
-                                "ms_per_launch": 1e3 * t_trace / n_launch, "nodes_per_segment": per_seg_nodes, "tris_per_segment": per_seg_tris,
+        "photon_trace_kernel": {"seconds": t_trace, "alg_bytes": bytes_trace, "gbps": bytes_trace / t_trace / 1e9, "launches": 6 * n_launch,
+                                "ms_per_round": 1e3 * t_trace, "nodes_per_segment": per_seg_nodes, "tris_per_segment": per_seg_tris,
                                 "segments_per_s": seg / t_trace},
         "photon_deposit_kernel": {"seconds": t_dep, "alg_bytes": bytes_dep, "gbps": bytes_dep / t_dep / 1e9, "launches": n_launch,
                                   "ms_per_launch": 1e3 * t_dep / n_launch, "candidates_per_hit": cand / max(1, hits),
                                   "deposits_per_hit": dep / max(1, hits), "hits_per_s": hits / t_dep},
+        "bin_scan+bin_scatter_kernel": {"seconds": t_sort, "launches": 3 * n_launch},
         "round_update_kernel": {"seconds": t_upd, "launches": 1},
     }
     dom = "photon_trace_kernel" if t_trace >= t_dep else "photon_deposit_kernel"
     roofline = {"bound": "hbm", "kernel": dom, "achieved": kernels[dom]["gbps"], "peak": peak, "unit": "GB/s", "frac": kernels[dom]["gbps"] / peak,
-                "traffic": None, "peak_source": peak_src, "share_of_step": kernels[dom]["seconds"] / (t_trace + t_dep + t_upd),
+                "traffic": None, "peak_source": peak_src, "share_of_step": kernels[dom]["seconds"] / (t_trace + t_dep + t_sort + t_upd),
                 "other_kernel": {k: {"achieved": v["gbps"], "frac": v["gbps"] / peak} for k, v in kernels.items() if k != dom and "gbps" in v},
                 "note": "algorithmic bytes per SURVEY 8(d) record sizes x counters of the profiled round / CUDA-event durations; the working set "
                         "(BVH 16 MB, hitpoint prefilter 18 MB + exact records 72 MB, cell table 4 MB) is L2-resident, so the algorithmic "
@@ -293,7 +295,7 @@ def run_gpu(args):
         "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
         "config": {"workload": WORKLOAD, "width": WIDTH, "height": HEIGHT, "photons_per_gpu_per_step": P, "hitpoints": c2["hitpoints"],
                    "triangles": scene.num_triangles(), "accum": "f64 atomics" if args.accum == 0 else "v4.f32 red",
-                   "l2": "inputs larger than L2: every round streams a fresh 1.5 GB deposit queue per 4 Mi-photon chunk and new photons"},
+                   "l2": "inputs larger than L2: every round writes and re-reads a fresh 8 GB deposit table (16 Mi photons x 5 bounces x 96 B) and new photons"},
         "s_per_round": ms * 1e-3 / args.steps, "eye_rays_per_s": c0["eye_segments"] / (tm0["eye"] * 1e-3),
         "segments_per_s": (c2["photon_segments"] - c1["photon_segments"]) * world / (ms * 1e-3),
         "setup": {"commit_s": t_commit, "eye_ms": tm0["eye"], "grid_ms": tm0["grid"], "eye_segments": c0["eye_segments"]},

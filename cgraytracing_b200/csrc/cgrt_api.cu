@@ -906,19 +906,25 @@ int cgrt_photon_pass(cgrt_ctx *ctx, uint64_t first, uint64_t count) {
         CK(cudaMemsetAsync(ctx->dep_hist, 0, (size_t)CGRT_NBINS * sizeof(uint32_t), ctx->stream));
         CK(cudaMemsetAsync(ctx->d_qcount + 2, 0, 6 * sizeof(unsigned int), ctx->stream));
         unsigned int *qc = ctx->d_qcount + 2;
-#define LAUNCH_PT(F, C, GRID, QIN, NIN, QOUT, NOUT)                                                                                           \
-    photon_trace_kernel<F, C><<<GRID, CGRT_TRACE_BLOCK, 0, ctx->stream>>>(ctx->S, P, base, (unsigned int)n, QIN, NIN, QOUT, NOUT, ctx->dep_rec, \
-                                                                          ctx->dep_keys, ctx->dep_hist, ctx->d_ctr, ctx->d_tc)
-        if (ctx->counting) LAUNCH_PT(true, true, nblk(n, CGRT_TRACE_BLOCK), nullptr, nullptr, ctx->pq[0], qc);
-        else LAUNCH_PT(true, false, nblk(n, CGRT_TRACE_BLOCK), nullptr, nullptr, ctx->pq[0], qc);
+#define LAUNCH_PT(F, GRID, QIN, NIN, QOUT, NOUT)                                                                                       \
+    do {                                                                                                                                   \
+        if (ctx->S.nbez > 0)                                                                                                               \
+            photon_trace_kernel<F, true><<<GRID, CGRT_TRACE_BLOCK, 0, ctx->stream>>>(ctx->S, P, base, (unsigned int)n, QIN, NIN, QOUT, NOUT,  \
+                                                                                     ctx->dep_rec, ctx->dep_keys, ctx->dep_hist, ctx->d_ctr); \
+        else                                                                                                                               \
+            photon_trace_kernel<F, false><<<GRID, CGRT_TRACE_BLOCK, 0, ctx->stream>>>(ctx->S, P, base, (unsigned int)n, QIN, NIN, QOUT, NOUT, \
+                                                                                      ctx->dep_rec, ctx->dep_keys, ctx->dep_hist, ctx->d_ctr); \
+    } while (0)
+        LAUNCH_PT(true, nblk(n, CGRT_TRACE_BLOCK), nullptr, nullptr, ctx->pq[0], qc);
         ctx->launches++;
         if (ctx->S.nbvh > 0) {
             for (int pass = 1; pass <= P.max_depth; pass++) {  // a resumed photon advances at least one segment per pass
-                const PhotonState *qin = ctx->pq[(pass - 1) & 1];
+                PhotonState *qin = ctx->pq[(pass - 1) & 1];
                 PhotonState *qout = ctx->pq[pass & 1];
-                if (ctx->counting) LAUNCH_PT(false, true, resume_grid, qin, qc + pass - 1, qout, qc + pass);
-                else LAUNCH_PT(false, false, resume_grid, qin, qc + pass - 1, qout, qc + pass);
-                ctx->launches++;
+                if (ctx->counting) photon_traverse_kernel<true><<<resume_grid, 128, 0, ctx->stream>>>(ctx->S, qin, qc + pass - 1, ctx->d_tc);
+                else photon_traverse_kernel<false><<<resume_grid, 128, 0, ctx->stream>>>(ctx->S, qin, qc + pass - 1, ctx->d_tc);
+                LAUNCH_PT(false, resume_grid, qin, qc + pass - 1, qout, qc + pass);
+                ctx->launches += 2;
             }
         }
 #undef LAUNCH_PT

@@ -520,7 +520,9 @@ struct HitAcc {
     d3 nrm;
 };
 
-// phase 1: analytic primitives of one ray, in object order
+// phase 1: analytic primitives of one ray, in object order. BEZ = false compiles the Newton solver out (scenes without a
+// Bezier object: the solver's local arrays and registers would otherwise tax every kernel that inlines this).
+template <bool BEZ = true>
 __device__ __forceinline__ void analytic_phase(const SceneDev &S, d3 o, d3 d, HitAcc &A) {
     A.nearest = CGRT_INF; A.id = -1; A.prim = -1; A.nrm = mk(0, 0, 0);
     for (int i = 0; i < S.nobj; i++) {
@@ -545,7 +547,7 @@ __device__ __forceinline__ void analytic_phase(const SceneDev &S, d3 o, d3 d, Hi
                     }
                 }
             }
-        } else if (O.kind == OBJ_BEZIER) {
+        } else if (BEZ && O.kind == OBJ_BEZIER) {
             double len; d3 nv;
             if (bezier_intersect(S.bez[O.aux], o, d, len, nv)) {
                 if (len < A.nearest) { A.id = i; A.nearest = len; A.nrm = nv; A.prim = -1; }

@@ -265,9 +265,12 @@ struct __align__(32) DepositRec {
     int ix, iy, iz, pad0;            // hash.h:38-42 cell of pos
     double pad1;
 };
-struct __align__(16) PhotonState {   // a suspended photon
-    double o[3], d[3], flux[3];
+struct __align__(16) PhotonState {   // a suspended photon, 128 bytes
+    double o[3], d[3], flux[3];      // the ray it was about to trace and the flux it carries
+    double nearest, nrm[3];          // closest analytic hit so far (photon_traverse_kernel merges the meshes into it)
+    int id, prim;
     uint32_t local, depth;
+    double pad;
 };
 
 // Bin of a deposit: any well-mixed CGRT_BIN_BITS-bit function of the cell. It only brings the records of one cell next to
@@ -279,20 +282,59 @@ __device__ __forceinline__ uint32_t cell_bin(int ix, int iy, int iz) {
     return h & (CGRT_NBINS - 1u);
 }
 
-template <bool FIRST, bool COUNT>
+// The BVH part of the closest hit for suspended photons: one thread per queue entry, every lane traverses (dense warps,
+// small register footprint). The winner of (analytic hit, mesh hits) is written back into the entry.
+template <bool COUNT>
+__global__ void __launch_bounds__(128) photon_traverse_kernel(const __grid_constant__ SceneDev S, PhotonState *__restrict__ q,
+                                                              const unsigned int *__restrict__ n_in, TravCounters *tcg) {
+    const unsigned int total = *n_in;
+    TravCounters tcl;
+    tcl.node_visits = 0; tcl.tri_tests = 0;
+    for (unsigned int i = blockIdx.x * blockDim.x + threadIdx.x; i < total; i += gridDim.x * blockDim.x) {
+        const double2 *p = reinterpret_cast<const double2 *>(q + i);
+        double2 q0 = p[0], q1 = p[1], q2 = p[2];
+        d3 o = mk(q0.x, q0.y, q1.x), d = mk(q1.y, q2.x, q2.y);
+        HitAcc A;
+        A.nearest = q[i].nearest; A.id = q[i].id; A.prim = -1; A.nrm = mk(0, 0, 0);
+        bool changed = false;
+        for (int k = 0; k < S.nobj; k++) {
+            if (S.obj[k].bvh < 0) continue;
+            double lim;
+            if (!bvh_wanted(S, k, o, d, A, lim)) continue;
+            double t; int leaf;
+            if (bvh_closest<COUNT>(S.bvh[S.obj[k].bvh], o, d, lim, t, leaf, &tcl)) { bvh_merge(S, k, leaf, t, A); changed = true; }
+        }
+        if (changed) {
+            q[i].nearest = A.nearest;
+            q[i].nrm[0] = A.nrm.x; q[i].nrm[1] = A.nrm.y; q[i].nrm[2] = A.nrm.z;
+            q[i].id = A.id; q[i].prim = A.prim;
+        }
+    }
+    if (COUNT) {
+        unsigned int nn = (unsigned int)tcl.node_visits, nt_ = (unsigned int)tcl.tri_tests;
+#pragma unroll
+        for (int off = 16; off > 0; off >>= 1) { nn += __shfl_xor_sync(0xffffffffu, nn, off); nt_ += __shfl_xor_sync(0xffffffffu, nt_, off); }
+        if ((threadIdx.x & 31) == 0) {
+            if (nn) atomicAdd(&tcg->node_visits, (unsigned long long)nn);
+            if (nt_) atomicAdd(&tcg->tri_tests, (unsigned long long)nt_);
+        }
+    }
+}
+
+// Emission (FIRST) or continuation of suspended photons whose pending segment has been resolved by photon_traverse_kernel.
+template <bool FIRST, bool BEZ>
 __global__ void __launch_bounds__(CGRT_TRACE_BLOCK) photon_trace_kernel(const __grid_constant__ SceneDev S, const __grid_constant__ PassParams P,
                                                                         uint64_t first_index, unsigned int n, const PhotonState *__restrict__ qin,
                                                                         const unsigned int *__restrict__ n_in, PhotonState *__restrict__ qout,
                                                                         unsigned int *n_out, DepositRec *__restrict__ rec, uint32_t *__restrict__ keys,
-                                                                        uint32_t *__restrict__ hist, Counters *ctr, TravCounters *tcg) {
+                                                                        uint32_t *__restrict__ hist, Counters *ctr) {
     const unsigned int total = FIRST ? n : *n_in;
-    TravCounters tcl;
-    tcl.node_visits = 0; tcl.tri_tests = 0;
     unsigned int nseg = 0, nhit = 0;
     for (unsigned int i = blockIdx.x * CGRT_TRACE_BLOCK + threadIdx.x; i < total; i += gridDim.x * CGRT_TRACE_BLOCK) {
         d3 o, d, flux;
         unsigned int local;
         int depth;
+        HitAcc A;
         if (FIRST) {  // main.cpp:240-246
             local = i; depth = 0;
             Philox g;
@@ -304,26 +346,27 @@ __global__ void __launch_bounds__(CGRT_TRACE_BLOCK) photon_trace_kernel(const __
             flux = mk(700, 700, 700) * (CGRT_PI * 4.0);
         } else {
             const double2 *q = reinterpret_cast<const double2 *>(qin + i);
-            double2 q0 = __ldg(q), q1 = __ldg(q + 1), q2 = __ldg(q + 2), q3 = __ldg(q + 3), q4 = __ldg(q + 4);
+            double2 q0 = __ldg(q), q1 = __ldg(q + 1), q2 = __ldg(q + 2), q3 = __ldg(q + 3), q4 = __ldg(q + 4), q5 = __ldg(q + 5), q6 = __ldg(q + 6);
             o = mk(q0.x, q0.y, q1.x); d = mk(q1.y, q2.x, q2.y); flux = mk(q3.x, q3.y, q4.x);
-            uint64_t meta = (uint64_t)__double_as_longlong(q4.y);
+            A.nearest = q4.y; A.nrm = mk(q5.x, q5.y, q6.x);
+            long long ip = __double_as_longlong(q6.y);
+            A.id = (int)(uint32_t)ip; A.prim = (int)(uint32_t)(ip >> 32);
+            uint64_t meta = (uint64_t)__double_as_longlong(__ldg(reinterpret_cast<const double *>(q + 7)));
             local = (uint32_t)meta; depth = (int)(meta >> 32);
         }
         const uint64_t index = first_index + (uint64_t)local;
-        bool resume = !FIRST;  // the segment a suspended photon was waiting for: traverse here
+        bool resolved = !FIRST;  // a resumed photon arrives with the closest hit of its pending segment
         for (; depth < P.max_depth; depth++) {
-            HitAcc A;
-            analytic_phase(S, o, d, A);
             bool suspended = false;
-            for (int k = 0; k < S.nobj; k++) {
-                if (S.obj[k].bvh < 0) continue;
-                double lim;
-                if (!bvh_wanted(S, k, o, d, A, lim)) continue;
-                if (FIRST || !resume) { suspended = true; break; }
-                double t; int leaf;
-                if (bvh_closest<COUNT>(S.bvh[S.obj[k].bvh], o, d, lim, t, leaf, &tcl)) bvh_merge(S, k, leaf, t, A);
+            if (!resolved) {
+                analytic_phase<BEZ>(S, o, d, A);
+                for (int k = 0; k < S.nobj; k++) {
+                    double lim;
+                    if (S.obj[k].bvh >= 0 && bvh_wanted(S, k, o, d, A, lim)) { suspended = true; break; }
+                }
             }
-            {   // suspend: compact into the next queue
+            resolved = false;
+            {   // suspend in front of a mesh: compact into the next queue (warp ballot + one atomic per warp)
                 unsigned int act = __activemask();
                 unsigned int m = __ballot_sync(act, suspended);
                 if (suspended) {
@@ -333,12 +376,14 @@ __global__ void __launch_bounds__(CGRT_TRACE_BLOCK) photon_trace_kernel(const __
                     base = __shfl_sync(m, base, leader);
                     double2 *q = reinterpret_cast<double2 *>(qout + base + __popc(m & ((1u << lane) - 1u)));
                     uint64_t meta = ((uint64_t)(uint32_t)depth << 32) | (uint64_t)local;
+                    long long ip = ((long long)(uint32_t)A.prim << 32) | (long long)(uint32_t)A.id;
                     q[0] = make_double2(o.x, o.y); q[1] = make_double2(o.z, d.x); q[2] = make_double2(d.y, d.z);
-                    q[3] = make_double2(flux.x, flux.y); q[4] = make_double2(flux.z, __longlong_as_double((long long)meta));
+                    q[3] = make_double2(flux.x, flux.y); q[4] = make_double2(flux.z, A.nearest);
+                    q[5] = make_double2(A.nrm.x, A.nrm.y); q[6] = make_double2(A.nrm.z, __longlong_as_double(ip));
+                    q[7] = make_double2(__longlong_as_double((long long)meta), 0.0);
                 }
             }
             if (suspended) break;
-            resume = false;
             nseg++;
             if (A.id < 0) break;  // main.cpp:64-66
             d3 X = o + d * A.nearest;  // main.cpp:68
@@ -351,12 +396,11 @@ __global__ void __launch_bounds__(CGRT_TRACE_BLOCK) photon_trace_kernel(const __
                 const size_t slot = (size_t)depth * (size_t)n + (size_t)local;
                 int ix, iy, iz;
                 cell_coord(X, P.celllength, ix, iy, iz);
-                double4 *r = reinterpret_cast<double4 *>(rec + slot);
-                r[0] = make_double4(X.x, X.y, X.z, n_ff.x);
-                r[1] = make_double4(n_ff.y, n_ff.z, flux.x, flux.y);
-                int4 c = make_int4(ix, iy, iz, 0);
-                r[2] = make_double4(flux.z, __longlong_as_double(((long long)(uint32_t)c.y << 32) | (uint32_t)c.x),
-                                    __longlong_as_double((long long)(uint32_t)c.z), 0.0);
+                double2 *r = reinterpret_cast<double2 *>(rec + slot);  // streamed: written once, read once by the deposit kernel
+                __stcs(r, make_double2(X.x, X.y)); __stcs(r + 1, make_double2(X.z, n_ff.x));
+                __stcs(r + 2, make_double2(n_ff.y, n_ff.z)); __stcs(r + 3, make_double2(flux.x, flux.y));
+                __stcs(r + 4, make_double2(flux.z, __longlong_as_double(((long long)(uint32_t)iy << 32) | (uint32_t)ix)));
+                __stcs(r + 5, make_double2(__longlong_as_double((long long)(uint32_t)iz), 0.0));
                 const uint32_t bin = cell_bin(ix, iy, iz);
                 keys[slot] = bin;
                 atomicAdd(hist + bin, 1u);  // histogram of the counting sort, fused into the producer
@@ -390,20 +434,14 @@ __global__ void __launch_bounds__(CGRT_TRACE_BLOCK) photon_trace_kernel(const __
         }
     }
     // ---- counters: warp reduce, one atomic per warp and counter
-    unsigned int nn = COUNT ? (unsigned int)tcl.node_visits : 0u, nt_ = COUNT ? (unsigned int)tcl.tri_tests : 0u;
 #pragma unroll
     for (int off = 16; off > 0; off >>= 1) {
         nseg += __shfl_xor_sync(0xffffffffu, nseg, off);
         nhit += __shfl_xor_sync(0xffffffffu, nhit, off);
-        if (COUNT) { nn += __shfl_xor_sync(0xffffffffu, nn, off); nt_ += __shfl_xor_sync(0xffffffffu, nt_, off); }
     }
     if ((threadIdx.x & 31) == 0) {
         if (nseg) atomicAdd(&ctr->photon_segments, (unsigned long long)nseg);
         if (nhit) atomicAdd(&ctr->diffuse_hits, (unsigned long long)nhit);
-        if (COUNT) {
-            if (nn) atomicAdd(&tcg->node_visits, (unsigned long long)nn);
-            if (nt_) atomicAdd(&tcg->tri_tests, (unsigned long long)nt_);
-        }
     }
 }
 
@@ -422,9 +460,9 @@ __global__ void __launch_bounds__(CGRT_TRACE_BLOCK) photon_trace_kernel(const __
 #define CGRT_DEPOSIT_BLOCK 256
 #define CGRT_DEPOSIT_SPAN 128   /* sorted records per warp */
 
-__device__ __forceinline__ double4 ldg4(const double4 *p) {  // 32 bytes as two 16-byte read-only loads
+__device__ __forceinline__ double4 ldg4(const double4 *p) {  // 32 bytes of a deposit record: streamed (evict-first), two 16-byte loads
     const double2 *q = reinterpret_cast<const double2 *>(p);
-    double2 a = __ldg(q), b = __ldg(q + 1);
+    double2 a = __ldcs(q), b = __ldcs(q + 1);
     return make_double4(a.x, a.y, b.x, b.y);
 }
 
@@ -433,7 +471,7 @@ __device__ __forceinline__ void deposit_exact(const DepositRec *__restrict__ rec
                                               const double *__restrict__ hp_f, void *__restrict__ acc, unsigned int &ndep) {
     const double4 *r = reinterpret_cast<const double4 *>(rec + src);
     double4 r0 = ldg4(r), r1 = ldg4(r + 1);
-    double fz = __ldg(reinterpret_cast<const double *>(r + 2));
+    double fz = __ldcs(reinterpret_cast<const double *>(r + 2));
     const double2 *hp = reinterpret_cast<const double2 *>(hot + hidx);
     double2 a0 = __ldg(hp), a1 = __ldg(hp + 1), b0 = __ldg(hp + 2), b1 = __ldg(hp + 3);
     d3 X = mk(r0.x, r0.y, r0.z), nrm = mk(r0.w, r1.x, r1.y), flux = mk(r1.z, r1.w, fz);
@@ -483,7 +521,7 @@ __global__ void __launch_bounds__(CGRT_DEPOSIT_BLOCK) photon_deposit_kernel(cons
             float xf = 0, yf = 0, zf = 0;
             int ix = 0, iy = 0, iz = 0;
             if (valid) {
-                src = __ldg(perm + j);
+                src = __ldcs(perm + j);
                 const double4 *r = reinterpret_cast<const double4 *>(rec + src);
                 double4 r0 = ldg4(r), r2 = ldg4(r + 2);
                 xf = (float)r0.x; yf = (float)r0.y; zf = (float)r0.z;
