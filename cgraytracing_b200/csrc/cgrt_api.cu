@@ -85,6 +85,8 @@ struct cgrt_ctx {
     uint32_t *dep_hist = nullptr;     // CGRT_NBINS bin counters -> cursors
     uint32_t *dep_bsum = nullptr;     // per-4096-bin block totals
     uint32_t *dep_nvalid = nullptr;
+    uint32_t *reach = nullptr;        // reach bitmap (cells within 2 cells of a hitpoint), built with the grid
+    int cull = 1;
     Counters *d_ctr = nullptr;
     TravCounters *d_tc = nullptr;
     uint64_t launches = 0;
@@ -855,6 +857,10 @@ int cgrt_build_grid(cgrt_ctx *ctx) {
         CKS(radix_sort_dev(ctx, n, keys, 32 + kbits, keys_sorted, perm));
         hp_gather_sorted_kernel<<<nblk(n, 256), 256, 0, ctx->stream>>>(ctx->hp_rec, perm, n, P.r2_init, ctx->A, pixkeys, P.width);
         lower_bound_table_kernel<<<nblk((size_t)n + 1, 256), 256, 0, ctx->stream>>>(ctx->A.key, nullptr, n, P.hashsize, ctx->cell_start);
+        CKS(dalloc(ctx, &ctx->reach, (size_t)1 << (CGRT_REACH_BITS - 5)));
+        CK(cudaMemsetAsync(ctx->reach, 0, sizeof(uint32_t) << (CGRT_REACH_BITS - 5), ctx->stream));
+        reach_mark_kernel<<<nblk(n, 256), 256, 0, ctx->stream>>>(ctx->A.hot, n, P.celllength, ctx->reach);
+        ctx->launches++;
         ctx->launches += 2;
         int pbits = 1;
         while (pbits < 40 && ((uint64_t)npix >> pbits)) pbits++;
@@ -910,10 +916,10 @@ int cgrt_photon_pass(cgrt_ctx *ctx, uint64_t first, uint64_t count) {
     do {                                                                                                                                   \
         if (ctx->S.nbez > 0)                                                                                                               \
             photon_trace_kernel<F, true><<<GRID, CGRT_TRACE_BLOCK, 0, ctx->stream>>>(ctx->S, P, base, (unsigned int)n, QIN, NIN, QOUT, NOUT,  \
-                                                                                     ctx->dep_rec, ctx->dep_keys, ctx->dep_hist, ctx->d_ctr); \
+                                                                                     ctx->dep_rec, ctx->dep_keys, ctx->dep_hist, ctx->cull ? ctx->reach : nullptr, ctx->d_ctr); \
         else                                                                                                                               \
             photon_trace_kernel<F, false><<<GRID, CGRT_TRACE_BLOCK, 0, ctx->stream>>>(ctx->S, P, base, (unsigned int)n, QIN, NIN, QOUT, NOUT, \
-                                                                                      ctx->dep_rec, ctx->dep_keys, ctx->dep_hist, ctx->d_ctr); \
+                                                                                      ctx->dep_rec, ctx->dep_keys, ctx->dep_hist, ctx->cull ? ctx->reach : nullptr, ctx->d_ctr); \
     } while (0)
         LAUNCH_PT(true, nblk(n, CGRT_TRACE_BLOCK), nullptr, nullptr, ctx->pq[0], qc);
         ctx->launches++;
@@ -1123,6 +1129,12 @@ int cgrt_set_counting(cgrt_ctx *ctx, int on) {
     if (!ctx) return CGRT_ERR_INVALID;
     ctx->counting = on != 0;
     CK(cudaMemset(ctx->d_tc, 0, sizeof(TravCounters)));
+    return CGRT_OK;
+}
+
+int cgrt_set_culling(cgrt_ctx *ctx, int on) {
+    if (!ctx) return CGRT_ERR_INVALID;
+    ctx->cull = on != 0;
     return CGRT_OK;
 }
 

@@ -311,6 +311,8 @@ __device__ __forceinline__ bool root_box_hit(const BvhDev &B, d3 o, d3 d, double
     return slab_any(B.root_lo[0], B.root_lo[1], B.root_lo[2], B.root_hi[0], B.root_hi[1], B.root_hi[2], r, tmax, __double2float_ru(tmax), tn);
 }
 
+// (A "while-while" ordering that parks lanes on their leaf until the warp reconverges was measured slower here: 8.8 ms
+// vs 7.0 ms per 16 Mi-photon round for the traversal launches, 5.3 vs 7.5 live lanes per instruction.)
 template <bool COUNT>
 __device__ __forceinline__ bool bvh_closest(const BvhDev &B, d3 o, d3 d, double tmax, double &t_out, int &leaf_out, TravCounters *tc) {
     SlabRay R = make_slab_ray(o, d, B.f32_ok != 0);

@@ -240,6 +240,34 @@ __global__ void lower_bound_table_kernel(const uint32_t *__restrict__ keys32, co
 }
 
 // =================================================================================================================
+// Reach map: a bitmap over (hashed) cell coordinates that is set for every cell within +-2 cells of a hitpoint's cell.
+// A photon hit can only ever be accepted by a hitpoint at distance <= r0 = 200/height <= 1.0045 cells (main.cpp:116 with
+// r2 <= r0^2), i.e. by a hitpoint at most 2 cells away on every axis — whichever bucket the hash put it in.
+// A hit whose cell is not in the map therefore deposits nothing, and the photon kernel drops it before it costs a record,
+// a sort slot and a 27-bucket gather (about half of all hits in the reference scenes land on the unobserved front part of
+// the room). Hash collisions in the bitmap only add false positives. cull = 0 disables it (counter parity tests).
+// =================================================================================================================
+#define CGRT_REACH_BITS 26  /* 64 Mi bits = 8 MB */
+__device__ __forceinline__ uint32_t reach_hash(int ix, int iy, int iz) {
+    uint32_t h = (uint32_t)ix * 0x8DA6B343u ^ (uint32_t)iy * 0xD8163841u ^ (uint32_t)iz * 0xCB1AB31Fu;
+    h ^= h >> 13; h *= 0x9E3779B1u; h ^= h >> 16;
+    return h & ((1u << CGRT_REACH_BITS) - 1u);
+}
+__global__ void reach_mark_kernel(const HpHot *__restrict__ hot, unsigned int n, double celllength, uint32_t *__restrict__ bitmap) {
+    unsigned int k = blockIdx.x * blockDim.x + threadIdx.x;
+    if (k >= n) return;
+    int ix, iy, iz;
+    cell_coord(mk(hot[k].px, hot[k].py, hot[k].pz), celllength, ix, iy, iz);
+    for (int a = -2; a <= 2; a++)
+        for (int b = -2; b <= 2; b++)
+            for (int c = -2; c <= 2; c++) {
+                uint32_t h = reach_hash(ix + a, iy + b, iz + c);
+                uint32_t bit = 1u << (h & 31u);
+                if (!(bitmap[h >> 5] & bit)) atomicOr(bitmap + (h >> 5), bit);
+            }
+}
+
+// =================================================================================================================
 // Photon pass (main.cpp:221-249 + the photon half of trace(), :101-128,:158-166).
 //
 // photon_trace_kernel<FIRST>: one thread owns one photon and keeps its ray in registers from bounce to bounce — there
@@ -327,7 +355,7 @@ __global__ void __launch_bounds__(CGRT_TRACE_BLOCK) photon_trace_kernel(const __
                                                                         uint64_t first_index, unsigned int n, const PhotonState *__restrict__ qin,
                                                                         const unsigned int *__restrict__ n_in, PhotonState *__restrict__ qout,
                                                                         unsigned int *n_out, DepositRec *__restrict__ rec, uint32_t *__restrict__ keys,
-                                                                        uint32_t *__restrict__ hist, Counters *ctr) {
+                                                                        uint32_t *__restrict__ hist, const uint32_t *__restrict__ reach, Counters *ctr) {
     const unsigned int total = FIRST ? n : *n_in;
     unsigned int nseg = 0, nhit = 0;
     for (unsigned int i = blockIdx.x * CGRT_TRACE_BLOCK + threadIdx.x; i < total; i += gridDim.x * CGRT_TRACE_BLOCK) {
@@ -396,6 +424,10 @@ __global__ void __launch_bounds__(CGRT_TRACE_BLOCK) photon_trace_kernel(const __
                 const size_t slot = (size_t)depth * (size_t)n + (size_t)local;
                 int ix, iy, iz;
                 cell_coord(X, P.celllength, ix, iy, iz);
+                nhit++;
+                bool reachable = true;
+                if (reach) { uint32_t h = reach_hash(ix, iy, iz); reachable = (__ldg(reach + (h >> 5)) >> (h & 31u)) & 1u; }
+                if (reachable) {
                 double2 *r = reinterpret_cast<double2 *>(rec + slot);  // streamed: written once, read once by the deposit kernel
                 __stcs(r, make_double2(X.x, X.y)); __stcs(r + 1, make_double2(X.z, n_ff.x));
                 __stcs(r + 2, make_double2(n_ff.y, n_ff.z)); __stcs(r + 3, make_double2(flux.x, flux.y));
@@ -404,7 +436,7 @@ __global__ void __launch_bounds__(CGRT_TRACE_BLOCK) photon_trace_kernel(const __
                 const uint32_t bin = cell_bin(ix, iy, iz);
                 keys[slot] = bin;
                 atomicAdd(hist + bin, 1u);  // histogram of the counting sort, fused into the producer
-                nhit++;
+                }
             }
             if (depth + 1 >= P.max_depth) break;
             if (mat == MAT_DIFFUSE) {  // main.cpp:126-127: uniform hemisphere, origin NOT offset, flux * f / max(f)
@@ -448,13 +480,13 @@ __global__ void __launch_bounds__(CGRT_TRACE_BLOCK) photon_trace_kernel(const __
 // ---------------------------------------------------------------------------------------------------------------------
 // photon_deposit_kernel: the 27-cell gather and deposit of main.cpp:103-125 over deposit records SORTED by cell.
 //
-// One warp owns a contiguous range of the sorted order. Per batch of 32 records it forms groups of records that lie in
-// the same cell; a group shares its candidate list (the hitpoints of the 3x3x3 buckets, read once per group instead of
-// once per photon hit): lanes hold 32 candidates at a time, the group's hit positions are broadcast by shuffle, and every
-// (hit, candidate) pair first passes a 16-byte fp32 prefilter {x, y, z, (r + E)^2} (E bounds the float rounding of both
-// positions: the filter can only pass too much). Surviving pairs (~10-15 %) are compacted into a per-warp shared-memory
-// queue and processed 32 at a time by ALL lanes with the reference's exact fp64 test (main.cpp:116) on the 64-byte exact
-// records, then deposited with atomics. Two of the 27 cells hashing to one bucket list it twice, like the reference
+// One warp owns a contiguous range of the cell-grouped order. A batch is 32 records, one per lane; the records of the
+// batch that lie in one cell form a group and share its candidate list (the hitpoints of the 3x3x3 buckets, read once per
+// group instead of once per photon hit): up to 64 candidates at a time are staged in shared memory as 16-byte fp32
+// prefilter records {x, y, z, (r + E)^2} (E bounds the float rounding of both positions: the filter can only pass too
+// much) and every lane tests its own hit against each of them from a shared-memory broadcast, collecting a 64-bit mask.
+// Surviving pairs (~10-15 %) are drained into a per-warp queue and processed 32 at a time by ALL lanes with the
+// reference's exact fp64 test (main.cpp:116) on the 64-byte exact records, then deposited with atomics. Two of the 27 cells hashing to one bucket list it twice, like the reference
 // (SURVEY Q13). ACC: 0 = fp64 atomics {dflux.xyz, m}; 1 = one red.global.add.v4.f32.
 // ---------------------------------------------------------------------------------------------------------------------
 #define CGRT_DEPOSIT_BLOCK 256
@@ -466,15 +498,16 @@ __device__ __forceinline__ double4 ldg4(const double4 *p) {  // 32 bytes of a de
     return make_double4(a.x, a.y, b.x, b.y);
 }
 
+struct HitShared {  // exact data of the 32 records of a warp's batch, structure of arrays (one 256-byte row per component)
+    double v[9][32];  // pos.xyz, nrm.xyz, flux.xyz
+};
+
 template <int ACC>
-__device__ __forceinline__ void deposit_exact(const DepositRec *__restrict__ rec, uint32_t src, uint32_t hidx, const HpHot *__restrict__ hot,
+__device__ __forceinline__ void deposit_exact(const HitShared &H, uint32_t hl, uint32_t hidx, const HpHot *__restrict__ hot,
                                               const double *__restrict__ hp_f, void *__restrict__ acc, unsigned int &ndep) {
-    const double4 *r = reinterpret_cast<const double4 *>(rec + src);
-    double4 r0 = ldg4(r), r1 = ldg4(r + 1);
-    double fz = __ldcs(reinterpret_cast<const double *>(r + 2));
     const double2 *hp = reinterpret_cast<const double2 *>(hot + hidx);
     double2 a0 = __ldg(hp), a1 = __ldg(hp + 1), b0 = __ldg(hp + 2), b1 = __ldg(hp + 3);
-    d3 X = mk(r0.x, r0.y, r0.z), nrm = mk(r0.w, r1.x, r1.y), flux = mk(r1.z, r1.w, fz);
+    d3 X = mk(H.v[0][hl], H.v[1][hl], H.v[2][hl]), nrm = mk(H.v[3][hl], H.v[4][hl], H.v[5][hl]);
     d3 hpos = mk(a0.x, a0.y, a1.x);
     double r2 = a1.y;
     d3 hn = mk(b0.x, b0.y, b1.x);
@@ -482,6 +515,7 @@ __device__ __forceinline__ void deposit_exact(const DepositRec *__restrict__ rec
     if ((dot(hn, nrm) > CGRT_EPS) && (dot(dd, dd) <= r2)) {  // main.cpp:116
         const double2 *fp = reinterpret_cast<const double2 *>(hp_f + 4 * (size_t)hidx);
         double2 f0 = __ldg(fp), f1 = __ldg(fp + 1);
+        d3 flux = mk(H.v[6][hl], H.v[7][hl], H.v[8][hl]);
         d3 cc = (mk(f0.x, f0.y, f1.x) * flux) * (1.0 / CGRT_PI);  // f.mul(flux) * (1/PI), main.cpp:122
         if (ACC == 0) {
             double *ap = reinterpret_cast<double *>(acc) + 4 * (size_t)hidx;
@@ -501,8 +535,16 @@ __global__ void __launch_bounds__(CGRT_DEPOSIT_BLOCK) photon_deposit_kernel(cons
                                                                             const uint32_t *__restrict__ cell_start,
                                                                             const float4 *__restrict__ pre, const HpHot *__restrict__ hot,
                                                                             const double *__restrict__ hp_f, void *__restrict__ acc, Counters *ctr) {
+    // per warp: 64 staged candidates (prefilter record + hitpoint index) and the queue of (record, hitpoint) pairs that
+    // passed the prefilter
+    __shared__ float4 cpre_all[CGRT_DEPOSIT_BLOCK / 32][64];
+    __shared__ uint32_t cidx_all[CGRT_DEPOSIT_BLOCK / 32][64];
     __shared__ uint2 queue_all[CGRT_DEPOSIT_BLOCK / 32][64];
+    __shared__ HitShared hit_all[CGRT_DEPOSIT_BLOCK / 32];
     const int lane = threadIdx.x & 31;
+    HitShared &H = hit_all[threadIdx.x >> 5];
+    float4 *cpre = cpre_all[threadIdx.x >> 5];
+    uint32_t *cidx = cidx_all[threadIdx.x >> 5];
     uint2 *queue = queue_all[threadIdx.x >> 5];
     const unsigned int lt = (1u << lane) - 1u;
     const size_t warp = ((size_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
@@ -515,24 +557,30 @@ __global__ void __launch_bounds__(CGRT_DEPOSIT_BLOCK) photon_deposit_kernel(cons
     for (size_t span = warp * CGRT_DEPOSIT_SPAN; span < n_slots; span += nwarps * CGRT_DEPOSIT_SPAN) {
         const size_t span_end = span + CGRT_DEPOSIT_SPAN < n_slots ? span + CGRT_DEPOSIT_SPAN : n_slots;
         for (size_t base = span; base < span_end; base += 32) {
+            // ---- lane = one deposit record of the batch
             const size_t j = base + lane;
-            bool valid = j < span_end;
-            uint32_t src = 0;
-            float xf = 0, yf = 0, zf = 0;
+            const bool valid = j < span_end;
+            float hx = 0, hy = 0, hz = 0;
             int ix = 0, iy = 0, iz = 0;
             if (valid) {
-                src = __ldcs(perm + j);
+                const uint32_t src = __ldcs(perm + j);
                 const double4 *r = reinterpret_cast<const double4 *>(rec + src);
-                double4 r0 = ldg4(r), r2 = ldg4(r + 2);
-                xf = (float)r0.x; yf = (float)r0.y; zf = (float)r0.z;
+                double4 r0 = ldg4(r), r1 = ldg4(r + 1), r2 = ldg4(r + 2);  // streamed once: the exact data goes to shared memory
+                hx = (float)r0.x; hy = (float)r0.y; hz = (float)r0.z;
                 long long cxy = __double_as_longlong(r2.y);
                 ix = (int)(uint32_t)cxy; iy = (int)(uint32_t)(cxy >> 32); iz = (int)(uint32_t)__double_as_longlong(r2.z);
+                H.v[0][lane] = r0.x; H.v[1][lane] = r0.y; H.v[2][lane] = r0.z;
+                H.v[3][lane] = r0.w; H.v[4][lane] = r1.x; H.v[5][lane] = r1.y;
+                H.v[6][lane] = r1.z; H.v[7][lane] = r1.w; H.v[8][lane] = r2.x;
             }
+            __syncwarp();
             unsigned int remaining = __ballot_sync(0xffffffffu, valid);
             while (remaining) {
+                // ---- group = the records of the batch that lie in the leader's cell
                 const int leader = __ffs(remaining) - 1;
                 const int cx = __shfl_sync(0xffffffffu, ix, leader), cy = __shfl_sync(0xffffffffu, iy, leader), cz = __shfl_sync(0xffffffffu, iz, leader);
-                const unsigned int grp = __ballot_sync(0xffffffffu, valid && ix == cx && iy == cy && iz == cz) & remaining;
+                const bool in_grp = valid && ix == cx && iy == cy && iz == cz;
+                const unsigned int grp = __ballot_sync(0xffffffffu, in_grp) & remaining;
                 remaining &= ~grp;
                 // the 27 bucket ranges of this cell (main.cpp:105-113)
                 uint32_t beg = 0, cnt = 0;
@@ -550,46 +598,80 @@ __global__ void __launch_bounds__(CGRT_DEPOSIT_BLOCK) photon_deposit_kernel(cons
                 const uint32_t excl = incl - cnt;
                 const uint32_t total = __shfl_sync(0xffffffffu, incl, 31);
                 cand_total += (lane == 0) ? (unsigned long long)total * (unsigned int)__popc(grp) : 0ull;
-                for (uint32_t c0 = 0; c0 < total; c0 += 32) {
-                    const uint32_t c = c0 + lane;
-                    // owner cell of candidate c = last lane < 27 whose excl <= c (shuffle binary search)
-                    int lo = 0;
+                for (uint32_t c0 = 0; c0 < total; c0 += 64) {
+                    // ---- stage up to 64 candidates of the concatenated bucket lists
 #pragma unroll
-                    for (int step = 16; step >= 1; step >>= 1) {
-                        int probe = lo + step;
-                        uint32_t e = __shfl_sync(0xffffffffu, excl, probe & 31);
-                        if (probe < 27 && e <= c) lo = probe;
+                    for (int h = 0; h < 2; h++) {
+                        const uint32_t c = c0 + 32 * h + lane;
+                        int lo = 0;  // owner bucket of candidate c = last lane < 27 whose excl <= c (shuffle binary search)
+#pragma unroll
+                        for (int step = 16; step >= 1; step >>= 1) {
+                            int probe = lo + step;
+                            uint32_t e = __shfl_sync(0xffffffffu, excl, probe & 31);
+                            if (probe < 27 && e <= c) lo = probe;
+                        }
+                        const uint32_t e_lo = __shfl_sync(0xffffffffu, excl, lo);
+                        const uint32_t b_lo = __shfl_sync(0xffffffffu, beg, lo);
+                        if (c < total) {
+                            const uint32_t hidx = b_lo + (c - e_lo);
+                            cpre[32 * h + lane] = __ldg(pre + hidx);
+                            cidx[32 * h + lane] = hidx;
+                        } else {
+                            cpre[32 * h + lane] = make_float4(0.f, 0.f, 0.f, -1.f);  // never passes
+                        }
                     }
-                    const uint32_t e_lo = __shfl_sync(0xffffffffu, excl, lo);
-                    const uint32_t b_lo = __shfl_sync(0xffffffffu, beg, lo);
-                    const bool have = c < total;
-                    const uint32_t hidx = have ? b_lo + (c - e_lo) : 0u;
-                    float4 q = have ? __ldg(pre + hidx) : make_float4(0.f, 0.f, 0.f, -1.f);
-                    for (unsigned int m = grp; m; m &= m - 1) {
-                        const int hl = __ffs(m) - 1;
-                        const float hx = __shfl_sync(0xffffffffu, xf, hl), hy = __shfl_sync(0xffffffffu, yf, hl), hz = __shfl_sync(0xffffffffu, zf, hl);
-                        const uint32_t hsrc = __shfl_sync(0xffffffffu, src, hl);
-                        const float ddx = q.x - hx, ddy = q.y - hy, ddz = q.z - hz;
-                        const bool pass = ddx * ddx + ddy * ddy + ddz * ddz <= q.w;
-                        const unsigned int pm = __ballot_sync(0xffffffffu, pass);
-                        if (pass) queue[qn + __popc(pm & lt)] = make_uint2(hsrc, hidx);
+                    __syncwarp();
+                    // ---- prefilter: every lane tests its own hit against the staged candidates (shared-memory broadcast)
+                    const int nc = (int)(total - c0 < 64u ? total - c0 : 64u);
+                    unsigned int m_lo = 0, m_hi = 0;
+#pragma unroll 8
+                    for (int k = 0; k < 32; k++) {
+                        if (k < nc) {
+                            const float4 q = cpre[k];
+                            const float ddx = q.x - hx, ddy = q.y - hy, ddz = q.z - hz;
+                            m_lo |= (fmaf(ddz, ddz, fmaf(ddy, ddy, ddx * ddx)) <= q.w) ? (1u << k) : 0u;
+                        }
+                    }
+                    if (nc > 32) {
+#pragma unroll 8
+                        for (int k = 0; k < 32; k++) {
+                            if (k + 32 < nc) {
+                                const float4 q = cpre[32 + k];
+                                const float ddx = q.x - hx, ddy = q.y - hy, ddz = q.z - hz;
+                                m_hi |= (fmaf(ddz, ddz, fmaf(ddy, ddy, ddx * ddx)) <= q.w) ? (1u << k) : 0u;
+                            }
+                        }
+                    }
+                    if (!((grp >> lane) & 1u)) { m_lo = 0; m_hi = 0; }
+                    // ---- drain: one surviving pair per lane and round into the queue; 32 queued pairs = one exact step
+                    while (__any_sync(0xffffffffu, (m_lo | m_hi) != 0u)) {
+                        const bool has = (m_lo | m_hi) != 0u;
+                        int b = 0;
+                        if (m_lo) { b = __ffs(m_lo) - 1; m_lo &= m_lo - 1; }
+                        else if (m_hi) { b = 32 + __ffs(m_hi) - 1; m_hi &= m_hi - 1; }
+                        const unsigned int pm = __ballot_sync(0xffffffffu, has);
+                        if (has) queue[qn + __popc(pm & lt)] = make_uint2((uint32_t)lane, cidx[b]);
                         qn += __popc(pm);
                         if (qn >= 32) {
                             __syncwarp();
-                            uint2 pr = queue[qn - 32 + lane];
+                            const uint2 pr = queue[qn - 32 + lane];
                             qn -= 32;
-                            deposit_exact<ACC>(rec, pr.x, pr.y, hot, hp_f, acc, ndep);
+                            deposit_exact<ACC>(H, pr.x, pr.y, hot, hp_f, acc, ndep);
                             __syncwarp();
                         }
                     }
+                    __syncwarp();  // cpre / cidx are restaged next
                 }
             }
+            // the queue refers to this batch's shared-memory hit data: flush it before the next batch overwrites them
+            __syncwarp();
+            if (lane < qn) {
+                const uint2 pr = queue[lane];
+                deposit_exact<ACC>(H, pr.x, pr.y, hot, hp_f, acc, ndep);
+            }
+            qn = 0;
+            __syncwarp();
         }
-    }
-    __syncwarp();
-    if (lane < qn) {
-        uint2 pr = queue[lane];
-        deposit_exact<ACC>(rec, pr.x, pr.y, hot, hp_f, acc, ndep);
     }
     // counters: warp-reduce then one atomic per warp
     unsigned long long dep_total = ndep;
