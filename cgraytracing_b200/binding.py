@@ -26,7 +26,7 @@ ABI_SYMBOLS = [
     "cgrt_intersect_batch", "cgrt_hash_keys", "cgrt_surface_color", "cgrt_object_triangles", "cgrt_sample", "cgrt_radix_sort",
     "cgrt_count_traversal", "cgrt_eye_pass", "cgrt_export_hitpoints_dev", "cgrt_import_hitpoints_dev", "cgrt_build_grid", "cgrt_photon_pass",
     "cgrt_accum_dev", "cgrt_allreduce_accum", "cgrt_round_update", "cgrt_gather_image", "cgrt_num_hitpoints", "cgrt_download_hitpoints",
-    "cgrt_download_accum", "cgrt_download_grid", "cgrt_get_counters", "cgrt_get_timings", "cgrt_set_counting", "cgrt_set_profiling", "cgrt_set_culling",
+    "cgrt_download_accum", "cgrt_download_grid", "cgrt_get_counters", "cgrt_get_timings", "cgrt_set_counting", "cgrt_set_profiling", "cgrt_set_culling", "cgrt_set_overlap",
 ]
 
 
@@ -284,6 +284,9 @@ class Context:
 
     def set_culling(self, on=True):
         self._ck(self.L.cgrt_set_culling(self.h, int(on)))
+
+    def set_overlap(self, on=True):
+        self._ck(self.L.cgrt_set_overlap(self.h, int(on)))
 
     def set_profiling(self, on=True):
         self._ck(self.L.cgrt_set_profiling(self.h, int(on)))

@@ -55,6 +55,12 @@ class GpuEngine:
         import torch
 
         self.ctx, self.device, self.torch = ctx, device, torch
+        # collectives are enqueued relative to the library's own stream: no host synchronisation between the photon pass, the
+        # all-reduce and the update
+        self.stream = torch.cuda.ExternalStream(ctx.stream(), device=torch.device("cuda", device))
+
+    def collective_scope(self):
+        return self.torch.cuda.stream(self.stream)
 
     def eye_pass(self, y0, y1):
         self.ctx.eye_pass(y0, y1)
@@ -67,7 +73,7 @@ class GpuEngine:
 
     def import_hitpoints(self, rec):
         rec = rec.contiguous()
-        self.torch.cuda.current_stream().synchronize()
+        self.torch.cuda.synchronize(self.device)
         self.ctx.import_hitpoints_dev(rec.data_ptr(), rec.shape[0])
 
     def build_grid(self):
@@ -80,12 +86,11 @@ class GpuEngine:
         self.ctx.photon_pass(first, count)
 
     def accum_tensor(self):
-        """The live accumulator buffer: reduced in place."""
-        self.ctx.synchronize()
+        """The live accumulator buffer: reduced in place, in stream order."""
         return self._acc
 
     def accum_commit(self, t):
-        self.torch.cuda.current_stream().synchronize()
+        pass
 
     def round_update(self):
         self.ctx.round_update()
@@ -134,10 +139,14 @@ class ShardedRenderer:
         if self.world > 1:
             import torch.distributed as dist
 
-            acc = self.e.accum_tensor()
-            if acc is not None and acc.numel():
-                dist.all_reduce(acc, group=self.group)
-                self.e.accum_commit(acc)
+            import contextlib
+
+            scope = self.e.collective_scope() if hasattr(self.e, "collective_scope") else contextlib.nullcontext()
+            with scope:
+                acc = self.e.accum_tensor()
+                if acc is not None and acc.numel():
+                    dist.all_reduce(acc, group=self.group)
+                    self.e.accum_commit(acc)
         self.e.round_update()
         self.rounds_done += 1
         self.emitted += photons_per_round
