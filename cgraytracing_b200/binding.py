@@ -57,7 +57,7 @@ def load_library():
     if _lib is None:
         if not os.path.exists(LIB_PATH):
             raise CgrtError(f"{LIB_PATH} is missing: build it with `python -c 'import __graft_entry__ as g; g.build()'`; there is no CPU fallback")
-        L = C.CDLL(LIB_PATH)
+        L = C.CDLL(os.environ.get("CGRT_LIB", LIB_PATH))  # CGRT_LIB: dev override for A/B builds of the same library
         L.cgrt_last_error.restype = C.c_char_p
         L.cgrt_last_error.argtypes = [C.c_void_p]
         L.cgrt_create.argtypes = [C.c_int, C.POINTER(C.c_void_p)]

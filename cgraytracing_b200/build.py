@@ -37,7 +37,9 @@ def needs_build() -> bool:
 def build(force: bool = False, verbose: bool = False) -> str:
     if not force and not needs_build():
         return OUT
-    cmd = [nvcc_path()] + NVCC_FLAGS + (["-Xptxas", "-v"] if verbose else []) + ["-o", OUT, SRC]
+    extra = os.environ.get("CGRT_NVCC_EXTRA", "").split()  # dev: e.g. -DCGRT_TRACE_MINB=6 for launch-bound experiments
+    out = os.environ.get("CGRT_BUILD_OUT", OUT)
+    cmd = [nvcc_path()] + NVCC_FLAGS + extra + (["-Xptxas", "-v"] if verbose else []) + ["-o", out, SRC]
     env = dict(os.environ)
     env.pop("CXX", None)  # the image's CXX wrapper lacks an OpenMP spec; nvcc should use g++ from PATH
     env.pop("CC", None)

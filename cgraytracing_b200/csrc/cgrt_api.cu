@@ -93,6 +93,8 @@ struct cgrt_ctx {
     unsigned int chunk_seq = 0;
     cudaStream_t tstream = nullptr;
     int overlap = 1;
+    // resident-grid sizes of the persistent photon kernels (SMs x occupancy), so that static striding leaves no tail of late blocks
+    unsigned int grid_first = 592, grid_first_bez = 592, grid_cont = 592, grid_cont_bez = 592;
     PhotonState *pq[2] = {nullptr, nullptr};
     size_t pq_cap = 0;
     uint32_t *reach = nullptr;        // reach bitmap (cells within 2 cells of a hitpoint), built with the grid
@@ -391,6 +393,7 @@ void derive_params(cgrt_ctx *ctx) {
     double r = 200.0 / c.height;
     int cells = (int)(std::ceil(70.0 / r));
     P.celllength = 70.0 / cells;
+    P.inv_celllength = 1.0 / P.celllength;
     P.r2_init = r * r;
     P.alpha = c.alpha; P.focus_plane = c.focus_plane; P.lens_radius = c.lens_radius;
     for (int i = 0; i < 3; i++) { P.cam[i] = c.camorg[i]; P.light[i] = c.lightorg[i]; }
@@ -440,6 +443,16 @@ int cgrt_create(int device, cgrt_ctx **out) {
     {
         int sms = 0;
         if (cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, device) == cudaSuccess && sms > 0) ctx->deposit_grid = (unsigned int)sms * 8u;
+    }
+    {
+        int sms = 148, nb = 0;
+        cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, device);
+        auto occ = [&](const void *k) { return (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, k, CGRT_TRACE_BLOCK, 0) == cudaSuccess && nb > 0) ? (unsigned int)(nb * sms) : 592u; };
+        ctx->grid_first = occ((const void *)photon_trace_kernel<true, false>);
+        ctx->grid_first_bez = occ((const void *)photon_trace_kernel<true, true>);
+        ctx->grid_cont = occ((const void *)photon_trace_kernel<false, false>);
+        ctx->grid_cont_bez = occ((const void *)photon_trace_kernel<false, true>);
+        cudaGetLastError();
     }
     cgrt_default_config(&ctx->cfg);
     derive_params(ctx);
@@ -965,7 +978,11 @@ int cgrt_photon_pass(cgrt_ctx *ctx, uint64_t first, uint64_t count) {
             photon_trace_kernel<F, false><<<GRID, CGRT_TRACE_BLOCK, 0, T>>>(ctx->S, P, base, (unsigned int)n, QIN, NIN, QOUT, NOUT, B.rec,   \
                                                                             B.keys, B.hist, ctx->cull ? ctx->reach : nullptr, ctx->d_ctr); \
     } while (0)
-        LAUNCH_PT(true, nblk(n, CGRT_TRACE_BLOCK), nullptr, nullptr, ctx->pq[0], qc);
+        {
+            unsigned int want = nblk(n, CGRT_TRACE_BLOCK);
+            unsigned int g0 = ctx->S.nbez > 0 ? ctx->grid_first_bez : ctx->grid_first;
+            LAUNCH_PT(true, (want < g0 ? want : g0), nullptr, nullptr, ctx->pq[0], qc);
+        }
         ctx->launches++;
         if (ctx->S.nbvh > 0) {
             for (int pass = 1; pass <= P.max_depth; pass++) {  // a resumed photon advances at least one segment per pass
@@ -973,7 +990,7 @@ int cgrt_photon_pass(cgrt_ctx *ctx, uint64_t first, uint64_t count) {
                 PhotonState *qout = ctx->pq[pass & 1];
                 if (ctx->counting) photon_traverse_kernel<true><<<resume_grid, 128, 0, T>>>(ctx->S, qin, qc + pass - 1, ctx->d_tc);
                 else photon_traverse_kernel<false><<<resume_grid, 128, 0, T>>>(ctx->S, qin, qc + pass - 1, ctx->d_tc);
-                LAUNCH_PT(false, resume_grid, qin, qc + pass - 1, qout, qc + pass);
+                LAUNCH_PT(false, (ctx->S.nbez > 0 ? ctx->grid_cont_bez : ctx->grid_cont), qin, qc + pass - 1, qout, qc + pass);
                 ctx->launches += 2;
             }
         }

@@ -277,7 +277,8 @@ __device__ __forceinline__ SlabRay make_slab_ray(d3 o, d3 d, bool f32_ok) {
     SlabRay r;
     r.exact = !(f32_ok && fabs(o.x) <= CGRT_F32_BOUND && fabs(o.y) <= CGRT_F32_BOUND && fabs(o.z) <= CGRT_F32_BOUND);
     r.o = o;
-    r.id = mk(1.0 / d.x, 1.0 / d.y, 1.0 / d.z);
+    r.id = mk(0, 0, 0);
+    if (r.exact) r.id = mk(1.0 / d.x, 1.0 / d.y, 1.0 / d.z);  // three fp64 divisions: only for the rare far-origin ray
     r.ox = (float)o.x; r.oy = (float)o.y; r.oz = (float)o.z;
     r.ix = 1.0f / (float)d.x; r.iy = 1.0f / (float)d.y; r.iz = 1.0f / (float)d.z;
     return r;
@@ -654,11 +655,20 @@ __device__ __forceinline__ d3 surface_color(const SceneDev &S, int obj, d3 point
     return mk((double)tx.x / 256.0, (double)tx.y / 256.0, (double)tx.z / 256.0);
 }
 
-// hash.h:35-42
-__host__ __device__ __forceinline__ void cell_coord(d3 p, double celllength, int &ix, int &iy, int &iz) {
-    ix = (int)floor((p.x - (-35.0)) / celllength);
-    iy = (int)floor((p.y - (-35.0)) / celllength);
-    iz = (int)floor((p.z - (-15.0)) / celllength);
+// hash.h:35-42: ix = (int)floor((x - XMIN) / celllength). The quotient is first formed with a reciprocal multiply (|error| <= 2 ulp);
+// floor() of it equals floor() of the IEEE quotient unless the product lies within a few ulp of an integer, and only then is the
+// division actually performed. Same integers as the reference, three fp64 divisions fewer on almost every call.
+__host__ __device__ __forceinline__ int cell_floor_div(double num, double den, double inv_den) {
+    double q = num * inv_den;
+    double f = floor(q);
+    double tol = fabs(q) * 1e-15 + 1e-300;
+    if (q - f < tol || (f + 1.0) - q < tol) f = floor(num / den);
+    return (int)f;
+}
+__host__ __device__ __forceinline__ void cell_coord(d3 p, double celllength, double inv, int &ix, int &iy, int &iz) {
+    ix = cell_floor_div(p.x - (-35.0), celllength, inv);
+    iy = cell_floor_div(p.y - (-35.0), celllength, inv);
+    iz = cell_floor_div(p.z - (-15.0), celllength, inv);
 }
 __host__ __device__ __forceinline__ uint32_t cell_hash(int ix, int iy, int iz, uint32_t hashsize) {
     return (((uint32_t)ix * 73856093u) ^ ((uint32_t)iy * 19349663u) ^ ((uint32_t)iz * 83492791u)) % hashsize;

@@ -34,6 +34,7 @@ struct PassParams {
     int width, height, max_depth, samples, use_dof;
     uint32_t hashsize;
     double celllength;     // Hashtable ctor result, hash.h:25-26
+    double inv_celllength; // 1 / celllength (cell_floor_div)
     double r2_init;        // (200/height)^2, main.cpp:84,94
     double alpha, focus_plane, lens_radius;
     double cam[3], light[3];
@@ -73,6 +74,13 @@ struct Counters {
 // main.cpp:252-254) whatever order the wavefront produced the hitpoints in.
 // =================================================================================================================
 #define CGRT_TRACE_BLOCK 128
+// minimum resident blocks per SM asked of ptxas for the photon kernels (register caps; tuned with A/B builds)
+#ifndef CGRT_TRACE_MINB
+#define CGRT_TRACE_MINB 1   /* 6 (80 registers) and 8 (64 registers, spills) were measured: no gain / slower */
+#endif
+#ifndef CGRT_TRAV_MINB
+#define CGRT_TRAV_MINB 8   /* 64 registers: 13.7 vs 15.1 ms of trace time per round; 6 (80 registers) gained nothing */
+#endif
 
 template <bool FIRST>
 __global__ void __launch_bounds__(CGRT_TRACE_BLOCK) eye_bounce_kernel(const __grid_constant__ SceneDev S, const __grid_constant__ PassParams P, int depth,
@@ -135,7 +143,7 @@ __global__ void __launch_bounds__(CGRT_TRACE_BLOCK) eye_bounce_kernel(const __gr
     unsigned int hs = warp_claim(mk_hp, hp_count);
     if (mk_hp && hs < hp_cap) {
         int ix, iy, iz;
-        cell_coord(X, P.celllength, ix, iy, iz);
+        cell_coord(X, P.celllength, P.inv_celllength, ix, iy, iz);
         uint32_t key = cell_hash(ix, iy, iz, P.hashsize);
         uint64_t sortkey = ((uint64_t)key << 32) | (uint64_t)(path * 16u + (code & 15u));
         uint32_t pix = path / (uint32_t)P.samples;
@@ -257,7 +265,7 @@ __global__ void reach_mark_kernel(const HpHot *__restrict__ hot, unsigned int n,
     unsigned int k = blockIdx.x * blockDim.x + threadIdx.x;
     if (k >= n) return;
     int ix, iy, iz;
-    cell_coord(mk(hot[k].px, hot[k].py, hot[k].pz), celllength, ix, iy, iz);
+    cell_coord(mk(hot[k].px, hot[k].py, hot[k].pz), celllength, 1.0 / celllength, ix, iy, iz);
     for (int a = -2; a <= 2; a++)
         for (int b = -2; b <= 2; b++)
             for (int c = -2; c <= 2; c++) {
@@ -313,7 +321,7 @@ __device__ __forceinline__ uint32_t cell_bin(int ix, int iy, int iz) {
 // The BVH part of the closest hit for suspended photons: one thread per queue entry, every lane traverses (dense warps,
 // small register footprint). The winner of (analytic hit, mesh hits) is written back into the entry.
 template <bool COUNT>
-__global__ void __launch_bounds__(128) photon_traverse_kernel(const __grid_constant__ SceneDev S, PhotonState *__restrict__ q,
+__global__ void __launch_bounds__(128, CGRT_TRAV_MINB) photon_traverse_kernel(const __grid_constant__ SceneDev S, PhotonState *__restrict__ q,
                                                               const unsigned int *__restrict__ n_in, TravCounters *tcg) {
     const unsigned int total = *n_in;
     TravCounters tcl;
@@ -350,72 +358,109 @@ __global__ void __launch_bounds__(128) photon_traverse_kernel(const __grid_const
 }
 
 // Emission (FIRST) or continuation of suspended photons whose pending segment has been resolved by photon_traverse_kernel.
+// Persistent threads with refill: a lane whose photon ends (absorbed at the last bounce, missed, or suspended in front of a
+// mesh) takes the next photon (FIRST) / queue entry in the same loop iteration, so the warp stays full instead of idling
+// until its longest-lived photon finishes (measured before: 19.7 of 32 lanes live in <FIRST>, 8 in the continuation).
+// One iteration = [generate a ray] -> [one segment]. The ray of a fresh photon and of a diffuse bounce both come from one
+// Philox block through the same code (a fresh photon spends two more draws on its position), so refilling adds no divergence.
+enum { PH_NEED = 0, PH_FRESH = 1, PH_DIFFUSE = 2, PH_HAVE_RAY = 3, PH_RESOLVED = 4 };
+
 template <bool FIRST, bool BEZ>
-__global__ void __launch_bounds__(CGRT_TRACE_BLOCK) photon_trace_kernel(const __grid_constant__ SceneDev S, const __grid_constant__ PassParams P,
+__global__ void __launch_bounds__(CGRT_TRACE_BLOCK, BEZ ? 1 : CGRT_TRACE_MINB) photon_trace_kernel(const __grid_constant__ SceneDev S, const __grid_constant__ PassParams P,
                                                                         uint64_t first_index, unsigned int n, const PhotonState *__restrict__ qin,
                                                                         const unsigned int *__restrict__ n_in, PhotonState *__restrict__ qout,
                                                                         unsigned int *n_out, DepositRec *__restrict__ rec, uint32_t *__restrict__ keys,
                                                                         uint32_t *__restrict__ hist, const uint32_t *__restrict__ reach, Counters *ctr) {
     const unsigned int total = FIRST ? n : *n_in;
+    const unsigned int stride = gridDim.x * CGRT_TRACE_BLOCK;
+    unsigned int next = blockIdx.x * CGRT_TRACE_BLOCK + threadIdx.x;
     unsigned int nseg = 0, nhit = 0;
-    for (unsigned int i = blockIdx.x * CGRT_TRACE_BLOCK + threadIdx.x; i < total; i += gridDim.x * CGRT_TRACE_BLOCK) {
-        d3 o, d, flux;
-        unsigned int local;
-        int depth;
-        HitAcc A;
-        if (FIRST) {  // main.cpp:240-246
-            local = i; depth = 0;
-            Philox g;
-            g.init(P.seed, PASS_PHOTON, first_index + (uint64_t)i, 0);
-            double a = g.u01() * 4 - 2;
-            double b = g.u01() * 4 - 2;
-            d = sample_sphere(g);
-            o = mk(P.light[0], P.light[1], P.light[2]) + mk(a, 0, b);
-            flux = mk(700, 700, 700) * (CGRT_PI * 4.0);
-        } else {
-            const double2 *q = reinterpret_cast<const double2 *>(qin + i);
-            double2 q0 = __ldg(q), q1 = __ldg(q + 1), q2 = __ldg(q + 2), q3 = __ldg(q + 3), q4 = __ldg(q + 4), q5 = __ldg(q + 5), q6 = __ldg(q + 6);
-            o = mk(q0.x, q0.y, q1.x); d = mk(q1.y, q2.x, q2.y); flux = mk(q3.x, q3.y, q4.x);
-            A.nearest = q4.y; A.nrm = mk(q5.x, q5.y, q6.x);
-            long long ip = __double_as_longlong(q6.y);
-            A.id = (int)(uint32_t)ip; A.prim = (int)(uint32_t)(ip >> 32);
-            uint64_t meta = (uint64_t)__double_as_longlong(__ldg(reinterpret_cast<const double *>(q + 7)));
-            local = (uint32_t)meta; depth = (int)(meta >> 32);
+    int mode = PH_NEED;
+    d3 o = mk(0, 0, 0), d = mk(0, 0, 1), flux = mk(0, 0, 0), n_ff = mk(0, 0, 1);
+    unsigned int local = 0;
+    int depth = 0;
+    HitAcc A;
+    A.nearest = CGRT_INF; A.id = -1; A.prim = -1; A.nrm = mk(0, 0, 0);
+    bool done = false;
+    for (;;) {
+        // All 32 lanes stay in the loop until the whole warp is out of work and meet here every iteration: without the explicit
+        // reconvergence point, lanes that finish a segment early run ahead and the warp falls apart into sub-warps for good.
+        __syncwarp();
+        // ---- stage 1: a ray for every lane
+        if (mode == PH_NEED && !done) {
+            if (next >= total) {
+                done = true;
+            } else if (FIRST) {
+                local = next; depth = 0;
+                mode = PH_FRESH;
+                next += stride;
+            } else {
+                const double2 *q = reinterpret_cast<const double2 *>(qin + next);
+                double2 q0 = __ldg(q), q1 = __ldg(q + 1), q2 = __ldg(q + 2), q3 = __ldg(q + 3), q4 = __ldg(q + 4), q5 = __ldg(q + 5), q6 = __ldg(q + 6);
+                o = mk(q0.x, q0.y, q1.x); d = mk(q1.y, q2.x, q2.y); flux = mk(q3.x, q3.y, q4.x);
+                A.nearest = q4.y; A.nrm = mk(q5.x, q5.y, q6.x);
+                long long ip = __double_as_longlong(q6.y);
+                A.id = (int)(uint32_t)ip; A.prim = (int)(uint32_t)(ip >> 32);
+                uint64_t meta = (uint64_t)__double_as_longlong(__ldg(reinterpret_cast<const double *>(q + 7)));
+                local = (uint32_t)meta; depth = (int)(meta >> 32);
+                mode = PH_RESOLVED;  // arrives with the closest hit of its pending segment
+                next += stride;
+            }
         }
+        if (__all_sync(0xffffffffu, done)) break;
         const uint64_t index = first_index + (uint64_t)local;
-        bool resolved = !FIRST;  // a resumed photon arrives with the closest hit of its pending segment
-        for (; depth < P.max_depth; depth++) {
-            bool suspended = false;
-            if (!resolved) {
-                analytic_phase<BEZ>(S, o, d, A);
-                for (int k = 0; k < S.nobj; k++) {
-                    double lim;
-                    if (S.obj[k].bvh >= 0 && bvh_wanted(S, k, o, d, A, lim)) { suspended = true; break; }
-                }
+        if (!done && (mode == PH_FRESH || mode == PH_DIFFUSE)) {
+            // main.cpp:240-246 (fresh: square emitter + uniform sphere) / main.cpp:126 (diffuse bounce: uniform hemisphere)
+            Philox g;
+            g.init(P.seed, PASS_PHOTON, index, (uint32_t)depth);
+            double u0 = g.u01(), u1 = g.u01();
+            double a = u0 * 4 - 2, b = u1 * 4 - 2;
+            if (mode == PH_FRESH) { u0 = g.u01(); u1 = g.u01(); }
+            double z = 1.0 - 2.0 * u0;  // sample_sphere on (u0, u1)
+            double sn, cs;
+            sincos2pi(u1, sn, cs);
+            double r = sqrt(1.0 - z * z);
+            d3 s = mk(r * cs, r * sn, z);
+            if (mode == PH_FRESH) {
+                o = mk(P.light[0], P.light[1], P.light[2]) + mk(a, 0, b);
+                d = s;
+                flux = mk(700, 700, 700) * (CGRT_PI * 4.0);
+            } else {
+                if (dot(s, n_ff) < 0) s = -s;  // sample_halfsphere
+                d = s;
             }
-            resolved = false;
-            {   // suspend in front of a mesh: compact into the next queue (warp ballot + one atomic per warp)
-                unsigned int act = __activemask();
-                unsigned int m = __ballot_sync(act, suspended);
-                if (suspended) {
-                    int lane = threadIdx.x & 31, leader = __ffs(m) - 1;
-                    unsigned int base = 0;
-                    if (lane == leader) base = atomicAdd(n_out, (unsigned int)__popc(m));
-                    base = __shfl_sync(m, base, leader);
-                    double2 *q = reinterpret_cast<double2 *>(qout + base + __popc(m & ((1u << lane) - 1u)));
-                    uint64_t meta = ((uint64_t)(uint32_t)depth << 32) | (uint64_t)local;
-                    long long ip = ((long long)(uint32_t)A.prim << 32) | (long long)(uint32_t)A.id;
-                    q[0] = make_double2(o.x, o.y); q[1] = make_double2(o.z, d.x); q[2] = make_double2(d.y, d.z);
-                    q[3] = make_double2(flux.x, flux.y); q[4] = make_double2(flux.z, A.nearest);
-                    q[5] = make_double2(A.nrm.x, A.nrm.y); q[6] = make_double2(A.nrm.z, __longlong_as_double(ip));
-                    q[7] = make_double2(__longlong_as_double((long long)meta), 0.0);
-                }
+        }
+        // ---- stage 2: one segment
+        bool suspended = false;
+        if (!done && mode != PH_RESOLVED) {
+            analytic_phase<BEZ>(S, o, d, A);
+            for (int k = 0; k < S.nobj; k++) {
+                double lim;
+                if (S.obj[k].bvh >= 0 && bvh_wanted(S, k, o, d, A, lim)) { suspended = true; break; }
             }
-            if (suspended) break;
-            nseg++;
-            if (A.id < 0) break;  // main.cpp:64-66
+        }
+        {   // suspend in front of a mesh: compact into the next queue (warp ballot + one atomic per warp)
+            unsigned int m = __ballot_sync(0xffffffffu, suspended);
+            if (suspended) {
+                int lane = threadIdx.x & 31, leader = __ffs(m) - 1;
+                unsigned int base = 0;
+                if (lane == leader) base = atomicAdd(n_out, (unsigned int)__popc(m));
+                base = __shfl_sync(m, base, leader);
+                double2 *q = reinterpret_cast<double2 *>(qout + base + __popc(m & ((1u << lane) - 1u)));
+                uint64_t meta = ((uint64_t)(uint32_t)depth << 32) | (uint64_t)local;
+                long long ip = ((long long)(uint32_t)A.prim << 32) | (long long)(uint32_t)A.id;
+                q[0] = make_double2(o.x, o.y); q[1] = make_double2(o.z, d.x); q[2] = make_double2(d.y, d.z);
+                q[3] = make_double2(flux.x, flux.y); q[4] = make_double2(flux.z, A.nearest);
+                q[5] = make_double2(A.nrm.x, A.nrm.y); q[6] = make_double2(A.nrm.z, __longlong_as_double(ip));
+                q[7] = make_double2(__longlong_as_double((long long)meta), 0.0);
+            }
+        }
+        const bool traced = !done && !suspended;
+        nseg += traced ? 1u : 0u;
+        if (traced && A.id >= 0) {
             d3 X = o + d * A.nearest;  // main.cpp:68
-            d3 n_old = A.nrm, n_ff = A.nrm;
+            d3 n_old = A.nrm;
+            n_ff = A.nrm;
             bool into = true;
             if (dot(n_ff, d) > 0) { n_ff = -n_ff; into = false; }  // main.cpp:73-76
             d3 f = surface_color(S, A.id, X);
@@ -423,33 +468,33 @@ __global__ void __launch_bounds__(CGRT_TRACE_BLOCK) photon_trace_kernel(const __
             if (mat == MAT_DIFFUSE) {  // the 27-cell gather of main.cpp:103-125 runs in photon_deposit_kernel
                 const size_t slot = (size_t)depth * (size_t)n + (size_t)local;
                 int ix, iy, iz;
-                cell_coord(X, P.celllength, ix, iy, iz);
+                cell_coord(X, P.celllength, P.inv_celllength, ix, iy, iz);
                 nhit++;
                 bool reachable = true;
                 if (reach) { uint32_t h = reach_hash(ix, iy, iz); reachable = (__ldg(reach + (h >> 5)) >> (h & 31u)) & 1u; }
                 if (reachable) {
-                double2 *r = reinterpret_cast<double2 *>(rec + slot);  // streamed: written once, read once by the deposit kernel
-                __stcs(r, make_double2(X.x, X.y)); __stcs(r + 1, make_double2(X.z, n_ff.x));
-                __stcs(r + 2, make_double2(n_ff.y, n_ff.z)); __stcs(r + 3, make_double2(flux.x, flux.y));
-                __stcs(r + 4, make_double2(flux.z, __longlong_as_double(((long long)(uint32_t)iy << 32) | (uint32_t)ix)));
-                __stcs(r + 5, make_double2(__longlong_as_double((long long)(uint32_t)iz), 0.0));
-                const uint32_t bin = cell_bin(ix, iy, iz);
-                keys[slot] = bin;
-                atomicAdd(hist + bin, 1u);  // histogram of the counting sort, fused into the producer
+                    double2 *r = reinterpret_cast<double2 *>(rec + slot);  // streamed: written once, read once by the deposit kernel
+                    __stcs(r, make_double2(X.x, X.y)); __stcs(r + 1, make_double2(X.z, n_ff.x));
+                    __stcs(r + 2, make_double2(n_ff.y, n_ff.z)); __stcs(r + 3, make_double2(flux.x, flux.y));
+                    __stcs(r + 4, make_double2(flux.z, __longlong_as_double(((long long)(uint32_t)iy << 32) | (uint32_t)ix)));
+                    __stcs(r + 5, make_double2(__longlong_as_double((long long)(uint32_t)iz), 0.0));
+                    const uint32_t bin = cell_bin(ix, iy, iz);
+                    keys[slot] = bin;
+                    atomicAdd(hist + bin, 1u);  // histogram of the counting sort, fused into the producer
                 }
             }
-            if (depth + 1 >= P.max_depth) break;
-            if (mat == MAT_DIFFUSE) {  // main.cpp:126-127: uniform hemisphere, origin NOT offset, flux * f / max(f)
-                Philox g;
-                g.init(P.seed, PASS_PHOTON, index, (uint32_t)depth + 1);
-                d = sample_halfsphere(g, n_ff);
+            if (depth + 1 >= P.max_depth) {
+                mode = PH_NEED;
+            } else if (mat == MAT_DIFFUSE) {  // main.cpp:126-127: uniform hemisphere (drawn in stage 1), origin NOT offset, flux * f / max(f)
                 double p = max3(f.x, f.y, f.z);
                 flux = f * flux * (1.0 / p);
                 o = X;
+                mode = PH_DIFFUSE;
             } else if (mat == MAT_MIRROR) {  // main.cpp:131-134
                 d = d - n_ff * 2.0 * dot(n_ff, d);
                 o = X + n_ff * CGRT_EPS;
                 flux = f * flux * S.obj[A.id].refl;
+                mode = PH_HAVE_RAY;
             } else {  // glass, main.cpp:140-164: 50/50 roulette, flux unchanged
                 double nc = 1.0, nt = 1.33, nnt = into ? nc / nt : nt / nc, ddn = dot(d, n_ff), cos2t;
                 d3 refl_dir = d - n_old * 2.0 * dot(n_old, d);
@@ -462,7 +507,11 @@ __global__ void __launch_bounds__(CGRT_TRACE_BLOCK) photon_trace_kernel(const __
                     if (g.u01() < 0.5) { o = X + n_ff * CGRT_EPS; d = refl_dir; }
                     else { o = X - n_ff * CGRT_EPS; d = refr_dir; }
                 }
+                mode = PH_HAVE_RAY;
             }
+            depth++;
+        } else if (!done) {
+            mode = PH_NEED;  // suspended, or the ray left the scene (main.cpp:64-66)
         }
     }
     // ---- counters: warp reduce, one atomic per warp and counter
@@ -846,7 +895,7 @@ __global__ void hash_keys_kernel(int64_t n, const double *__restrict__ pos, uint
     int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
     int ix, iy, iz;
-    cell_coord(mk(pos[3 * i], pos[3 * i + 1], pos[3 * i + 2]), celllength, ix, iy, iz);
+    cell_coord(mk(pos[3 * i], pos[3 * i + 1], pos[3 * i + 2]), celllength, 1.0 / celllength, ix, iy, iz);
     if (ixyz) { ixyz[3 * i] = ix; ixyz[3 * i + 1] = iy; ixyz[3 * i + 2] = iz; }
     if (key) key[i] = cell_hash(ix, iy, iz, hashsize);
 }
