@@ -26,10 +26,27 @@ sys.path.insert(0, ROOT)
 
 import numpy as np  # noqa: E402
 
+# BASELINE.json configs. The headline (default) is c3: it is the config the metric is quoted on and it fits one GPU.
+WORKLOADS = {
+    #  name                preset               width height photons/round rounds hashsize  dof samples
+    "c1_spheres_bezier": ("c1_spheres_bezier", 512, 512, 1 << 20, 10, 1000001, 0, 1),
+    "c2_bunny_chess": ("c2_bunny_chess", 1024, 1024, 4 << 20, 20, 1000001, 0, 1),
+    "c3_dragon_glass": ("c3_dragon_glass", 1024, 1024, 16 << 20, 50, 1000001, 0, 1),
+    "c4_bump_dof": ("c4_bump_dof", 1920, 1080, 16 << 20, 20, 1000001, 1, 4),
+    "c5_dragon_4096": ("c3_dragon_glass", 4096, 4096, 1 << 30, 1, 16777259, 0, 1),  # 1 Gi photons per round; hashsize raised
+}
 WORKLOAD = "c3_dragon_glass"
-WIDTH = HEIGHT = 1024
-PHOTONS_PER_ROUND = 16 * 1024 * 1024
-ROUNDS = 50
+PRESET, WIDTH, HEIGHT, PHOTONS_PER_ROUND, ROUNDS, HASHSIZE, USE_DOF, SAMPLES = WORKLOADS[WORKLOAD]
+
+
+def select_workload(name):
+    global WORKLOAD, PRESET, WIDTH, HEIGHT, PHOTONS_PER_ROUND, ROUNDS, HASHSIZE, USE_DOF, SAMPLES
+    WORKLOAD = name
+    PRESET, WIDTH, HEIGHT, PHOTONS_PER_ROUND, ROUNDS, HASHSIZE, USE_DOF, SAMPLES = WORKLOADS[name]
+
+
+def make_config(RenderConfig, **kw):
+    return RenderConfig(width=WIDTH, height=HEIGHT, hashsize=HASHSIZE, use_dof=USE_DOF, num_of_samples=SAMPLES, **kw)
 
 # algorithmic bytes per unit (layout-independent record sizes)
 B_SEGMENT, B_NODE, B_TRI = 80, 32, 48
@@ -120,8 +137,8 @@ def run_reference(args):
     from cgraytracing_b200.scene import RenderConfig, preset
     from oracle import binding as ob
 
-    scene = preset(WORKLOAD)
-    cfg = RenderConfig(width=WIDTH, height=HEIGHT, update_mode=1, into_rule=0)
+    scene = preset(PRESET)
+    cfg = make_config(RenderConfig, update_mode=1, into_rule=0)
     o = ob.Oracle(scene, cfg)
     threads = o.max_threads()
     o.eye_pass()
@@ -162,9 +179,9 @@ def run_gpu(args):
     torch.cuda.set_device(local)
     if world > 1:
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
-    scene = preset(WORKLOAD)
-    cfg = RenderConfig(width=WIDTH, height=HEIGHT)
-    P = args.photons
+    scene = preset(PRESET)
+    cfg = make_config(RenderConfig)
+    P = args.photons if args.photons > 0 else PHOTONS_PER_ROUND
     peak, peak_src = load_peaks()
 
     # ---- setup (untimed for `value`): scene upload + LBVH build, tile-sharded eye pass + all-gather, grid
@@ -177,6 +194,7 @@ def run_gpu(args):
     eng = GpuEngine(g, local)
     R = ShardedRenderer(eng, rank, world)
     R.eye(HEIGHT)
+    g.synchronize()
     tm0 = g.timings()
     c0 = g.counters()
 
@@ -187,7 +205,7 @@ def run_gpu(args):
             gc.set_config(cfg, accum_mode=args.accum)
             scene.build_into(gc); gc.commit(); gc.eye_pass(); gc.build_grid()
             gc.set_counting(True)
-            gc.photon_pass(0, 1 << 20)
+            gc.photon_pass(0, min(P, 1 << 20))
             cc = gc.counters()
             per_seg_nodes = cc["node_visits"] / cc["photon_segments"]
             per_seg_tris = cc["tri_tests"] / cc["photon_segments"]
@@ -236,6 +254,7 @@ def run_gpu(args):
 
     seg = cp1["photon_segments"] - cp0["photon_segments"]
     hits = cp1["diffuse_hits"] - cp0["diffuse_hits"]
+    gathered = cp1["gathered_hits"] - cp0["gathered_hits"]  # hits that went through the 27-cell gather (the rest were culled)
     cand = cp1["candidates"] - cp0["candidates"]
     dep = cp1["deposits"] - cp0["deposits"]
     t_trace = (tp1["photon_trace"] - tp0["photon_trace"]) * 1e-3
@@ -244,14 +263,14 @@ def run_gpu(args):
     n_launch = (P + (16 << 20) - 1) // (16 << 20)  # chunks per round (cgrt_ctx::photon_chunk)
     t_sort = (tp1["deposit_sort"] - tp0["deposit_sort"]) * 1e-3
     bytes_trace = seg * (B_SEGMENT + B_NODE * per_seg_nodes + B_TRI * per_seg_tris)
-    bytes_dep = hits * B_CELLS + cand * B_CAND + dep * B_DEP
+    bytes_dep = gathered * B_CELLS + cand * B_CAND + dep * B_DEP
     kernels = {
         "photon_trace_kernel": {"seconds": t_trace, "alg_bytes": bytes_trace, "gbps": bytes_trace / t_trace / 1e9, "launches": 6 * n_launch,
                                 "ms_per_round": 1e3 * t_trace, "nodes_per_segment": per_seg_nodes, "tris_per_segment": per_seg_tris,
                                 "segments_per_s": seg / t_trace},
         "photon_deposit_kernel": {"seconds": t_dep, "alg_bytes": bytes_dep, "gbps": bytes_dep / t_dep / 1e9, "launches": n_launch,
                                   "ms_per_launch": 1e3 * t_dep / n_launch, "candidates_per_hit": cand / max(1, hits),
-                                  "deposits_per_hit": dep / max(1, hits), "hits_per_s": hits / t_dep},
+                                  "deposits_per_hit": dep / max(1, hits), "hits_per_s": hits / t_dep, "diffuse_hits": hits, "gathered_hits": gathered},
         "bin_scan+bin_scatter_kernel": {"seconds": t_sort, "launches": 3 * n_launch},
         "round_update_kernel": {"seconds": t_upd, "launches": 1},
     }
@@ -288,7 +307,7 @@ def run_gpu(args):
                        f"grid + {args.e2e_rounds} rounds x {P} photons + updates + fp64 image and 8-bit image download, wall clock"}
 
     # ---- CPU baseline beside it (bounded sample)
-    cpu = cpu_baseline(scene, RenderConfig(width=WIDTH, height=HEIGHT, update_mode=1, into_rule=0), args.cpu_photons) if args.cpu_photons > 0 else None
+    cpu = cpu_baseline(scene, make_config(RenderConfig, update_mode=1, into_rule=0), args.cpu_photons) if args.cpu_photons > 0 else None
 
     line = {
         "metric": "photons_per_s", "value": value, "unit": "photons/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
@@ -313,12 +332,16 @@ def main():
     ap.add_argument("--steps", type=int, default=5)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
-    ap.add_argument("--photons", type=int, default=PHOTONS_PER_ROUND, help="photons per GPU per step (the named config uses 16 Mi)")
+    ap.add_argument("--workload", default=WORKLOAD, choices=sorted(WORKLOADS), help="BASELINE.json config (default: the headline config c3)")
+    ap.add_argument("--photons", type=int, default=0, help="photons per GPU per step (default: the workload's photons per round; c3 = 16 Mi)")
     ap.add_argument("--accum", type=int, default=1, help="0: fp64 atomics, 1: one v4.f32 red per deposit (SURVEY 8e: float32 x4 accumulators)")
     ap.add_argument("--cpu-photons", type=int, default=400000, help="photon budget of the CPU baseline sample (0 = skip)")
     ap.add_argument("--ref-photons", type=int, default=200000, help="photons per step of --impl reference")
-    ap.add_argument("--e2e-rounds", type=int, default=ROUNDS, help="rounds of the end-to-end render() (the named config has 50; 0 = skip)")
+    ap.add_argument("--e2e-rounds", type=int, default=-1, help="rounds of the end-to-end render() (default: the workload's own, c3 = 50; 0 = skip)")
     args = ap.parse_args()
+    select_workload(args.workload)
+    if args.e2e_rounds < 0:
+        args.e2e_rounds = ROUNDS
     if args.impl == "reference":
         run_reference(args)
     else:

@@ -94,7 +94,7 @@ struct cgrt_ctx {
     cudaStream_t tstream = nullptr;
     int overlap = 1;
     // resident-grid sizes of the persistent photon kernels (SMs x occupancy), so that static striding leaves no tail of late blocks
-    unsigned int grid_first = 592, grid_first_bez = 592, grid_cont = 592, grid_cont_bez = 592;
+    unsigned int grid_first = 592, grid_cont = 592;
     PhotonState *pq[2] = {nullptr, nullptr};
     size_t pq_cap = 0;
     uint32_t *reach = nullptr;        // reach bitmap (cells within 2 cells of a hitpoint), built with the grid
@@ -448,10 +448,8 @@ int cgrt_create(int device, cgrt_ctx **out) {
         int sms = 148, nb = 0;
         cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, device);
         auto occ = [&](const void *k) { return (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, k, CGRT_TRACE_BLOCK, 0) == cudaSuccess && nb > 0) ? (unsigned int)(nb * sms) : 592u; };
-        ctx->grid_first = occ((const void *)photon_trace_kernel<true, false>);
-        ctx->grid_first_bez = occ((const void *)photon_trace_kernel<true, true>);
-        ctx->grid_cont = occ((const void *)photon_trace_kernel<false, false>);
-        ctx->grid_cont_bez = occ((const void *)photon_trace_kernel<false, true>);
+        ctx->grid_first = occ((const void *)photon_trace_kernel<true>);
+        ctx->grid_cont = occ((const void *)photon_trace_kernel<false>);
         cudaGetLastError();
     }
     cgrt_default_config(&ctx->cfg);
@@ -969,28 +967,27 @@ int cgrt_photon_pass(cgrt_ctx *ctx, uint64_t first, uint64_t count) {
         CK(cudaMemsetAsync(B.hist, 0, (size_t)CGRT_NBINS * sizeof(uint32_t), T));
         CK(cudaMemsetAsync(ctx->d_qcount + 2, 0, 6 * sizeof(unsigned int), T));
         unsigned int *qc = ctx->d_qcount + 2;
-#define LAUNCH_PT(F, GRID, QIN, NIN, QOUT, NOUT)                                                                                          \
-    do {                                                                                                                                  \
-        if (ctx->S.nbez > 0)                                                                                                              \
-            photon_trace_kernel<F, true><<<GRID, CGRT_TRACE_BLOCK, 0, T>>>(ctx->S, P, base, (unsigned int)n, QIN, NIN, QOUT, NOUT, B.rec,    \
-                                                                           B.keys, B.hist, ctx->cull ? ctx->reach : nullptr, ctx->d_ctr);  \
-        else                                                                                                                              \
-            photon_trace_kernel<F, false><<<GRID, CGRT_TRACE_BLOCK, 0, T>>>(ctx->S, P, base, (unsigned int)n, QIN, NIN, QOUT, NOUT, B.rec,   \
-                                                                            B.keys, B.hist, ctx->cull ? ctx->reach : nullptr, ctx->d_ctr); \
-    } while (0)
+#define LAUNCH_PT(F, GRID, QIN, NIN, QOUT, NOUT)                                                                                    \
+    photon_trace_kernel<F><<<GRID, CGRT_TRACE_BLOCK, 0, T>>>(ctx->S, P, base, (unsigned int)n, QIN, NIN, QOUT, NOUT, B.rec, B.keys, B.hist, \
+                                                             ctx->cull ? ctx->reach : nullptr, ctx->d_ctr)
         {
             unsigned int want = nblk(n, CGRT_TRACE_BLOCK);
-            unsigned int g0 = ctx->S.nbez > 0 ? ctx->grid_first_bez : ctx->grid_first;
-            LAUNCH_PT(true, (want < g0 ? want : g0), nullptr, nullptr, ctx->pq[0], qc);
+            LAUNCH_PT(true, (want < ctx->grid_first ? want : ctx->grid_first), nullptr, nullptr, ctx->pq[0], qc);
         }
         ctx->launches++;
-        if (ctx->S.nbvh > 0) {
+        if (ctx->S.nbvh > 0 || ctx->S.nbez > 0) {
             for (int pass = 1; pass <= P.max_depth; pass++) {  // a resumed photon advances at least one segment per pass
                 PhotonState *qin = ctx->pq[(pass - 1) & 1];
                 PhotonState *qout = ctx->pq[pass & 1];
-                if (ctx->counting) photon_traverse_kernel<true><<<resume_grid, 128, 0, T>>>(ctx->S, qin, qc + pass - 1, ctx->d_tc);
-                else photon_traverse_kernel<false><<<resume_grid, 128, 0, T>>>(ctx->S, qin, qc + pass - 1, ctx->d_tc);
-                LAUNCH_PT(false, (ctx->S.nbez > 0 ? ctx->grid_cont_bez : ctx->grid_cont), qin, qc + pass - 1, qout, qc + pass);
+                const unsigned int *nin = qc + pass - 1;
+                if (ctx->S.nbez > 0) {  // the Newton solver costs registers: meshes-only scenes run the lean variant
+                    if (ctx->counting) photon_traverse_kernel<true, true><<<resume_grid, 128, 0, T>>>(ctx->S, qin, nin, ctx->d_tc);
+                    else photon_traverse_kernel<false, true><<<resume_grid, 128, 0, T>>>(ctx->S, qin, nin, ctx->d_tc);
+                } else {
+                    if (ctx->counting) photon_traverse_kernel<true, false><<<resume_grid, 128, 0, T>>>(ctx->S, qin, nin, ctx->d_tc);
+                    else photon_traverse_kernel<false, false><<<resume_grid, 128, 0, T>>>(ctx->S, qin, nin, ctx->d_tc);
+                }
+                LAUNCH_PT(false, ctx->grid_cont, qin, nin, qout, qc + pass);
                 ctx->launches += 2;
             }
         }
@@ -1185,6 +1182,7 @@ int cgrt_get_counters(cgrt_ctx *ctx, cgrt_counters *out) {
     out->diffuse_hits = c.diffuse_hits;
     out->candidates = c.candidates;
     out->deposits = c.deposits;
+    out->gathered_hits = c.gathered_hits;
     {
         TravCounters tc;
         CK(cudaMemcpy(&tc, ctx->d_tc, sizeof tc, cudaMemcpyDeviceToHost));

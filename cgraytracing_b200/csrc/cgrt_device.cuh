@@ -387,23 +387,26 @@ __device__ __forceinline__ bool box_any_face_hit(const double *b, d3 o, d3 d) { 
     return false;
 }
 
-// Bernstein value and derivative of the profile curve (bezier.h:30-40,127-142) by de Casteljau-free direct powers.
+// Bernstein value of the profile curve (bezier.h:30-35,127-134) and the reference's "gradient" (bezier.h:37-40,135-142):
+//   dB(n,i,t) = i * B(n-1,i-1,t) - (n-i) * B(n-1,i,t)
+// which is NOT the derivative n * (B(n-1,i-1) - B(n-1,i)) of the Bernstein basis (the correct form is commented out at
+// bezier.h:39). The reference's Newton Jacobian and its surface normals are built from this quantity, so the picture
+// depends on it and it is reproduced as is (gradP(0) = (0,32,-8), not 3*(P1-P0) = (0,36,0)).
 __device__ __forceinline__ void bez_eval(const BezDev &Z, double u, d3 &P, d3 &dP) {
     int n = Z.ncp - 1;
-    // binomial row
-    double C[CGRT_MAX_CP];
-    C[0] = 1.0;
+    double C[CGRT_MAX_CP], Cm[CGRT_MAX_CP];  // binomial rows n and n-1
+    C[0] = 1.0; Cm[0] = 1.0;
     for (int i = 1; i <= n; i++) C[i] = C[i - 1] * (double)(n - i + 1) / (double)i;
+    for (int i = 1; i <= n - 1; i++) Cm[i] = Cm[i - 1] * (double)(n - i) / (double)i;
     double pu[CGRT_MAX_CP], pv[CGRT_MAX_CP];
     pu[0] = 1.0; pv[0] = 1.0;
     for (int i = 1; i <= n; i++) { pu[i] = pu[i - 1] * u; pv[i] = pv[i - 1] * (1.0 - u); }
     P = mk(0, 0, 0); dP = mk(0, 0, 0);
     for (int i = 0; i <= n; i++) {
         double b = C[i] * pv[n - i] * pu[i];
-        // d/du [u^i (1-u)^(n-i)] = i u^(i-1) (1-u)^(n-i) - (n-i) u^i (1-u)^(n-i-1)
         double db = 0.0;
-        if (i > 0) db += C[i] * (double)i * pu[i - 1] * pv[n - i];
-        if (i < n) db -= C[i] * (double)(n - i) * pu[i] * pv[n - i - 1];
+        if (i > 0) db += Cm[i - 1] * pv[n - i] * pu[i - 1] * (double)i;          // B(n-1, i-1, u) * i
+        if (i < n) db -= Cm[i] * pv[n - 1 - i] * pu[i] * (double)(n - i);        // B(n-1, i, u) * (n-i)
         d3 c = mk(Z.cp[i][0], Z.cp[i][1], Z.cp[i][2]);
         P = P + c * b;
         dP = dP + c * db;
@@ -502,7 +505,9 @@ template <int BLOCK>
 struct TraceShared {
     double ox[BLOCK], oy[BLOCK], oz[BLOCK], dx[BLOCK], dy[BLOCK], dz[BLOCK];
     double lim[BLOCK];            // in: traversal limit of the listed ray; out: closest t
-    int leaf[BLOCK];              // out: sorted triangle position or -1
+    int leaf[BLOCK];              // out: 1 if the deferred object won
+    double near_in[BLOCK];        // in: nearest so far
+    int id_in[BLOCK];             // in: its object id; out: primitive id of the new hit
     unsigned short list[BLOCK];   // compacted thread slots
     unsigned int count;
     unsigned int scratch[8];      // per-kernel block aggregates
@@ -523,9 +528,8 @@ struct HitAcc {
     d3 nrm;
 };
 
-// phase 1: analytic primitives of one ray, in object order. BEZ = false compiles the Newton solver out (scenes without a
-// Bezier object: the solver's local arrays and registers would otherwise tax every kernel that inlines this).
-template <bool BEZ = true>
+// phase 1: the cheap analytic primitives of one ray (planes, spheres), in object order. Meshes, displaced floors and Bezier
+// surfaces are "deferred objects": phase 2 resolves them with the lanes that actually need them packed densely.
 __device__ __forceinline__ void analytic_phase(const SceneDev &S, d3 o, d3 d, HitAcc &A) {
     A.nearest = CGRT_INF; A.id = -1; A.prim = -1; A.nrm = mk(0, 0, 0);
     for (int i = 0; i < S.nobj; i++) {
@@ -550,18 +554,15 @@ __device__ __forceinline__ void analytic_phase(const SceneDev &S, d3 o, d3 d, Hi
                     }
                 }
             }
-        } else if (BEZ && O.kind == OBJ_BEZIER) {
-            double len; d3 nv;
-            if (bezier_intersect(S.bez[O.aux], o, d, len, nv)) {
-                if (len < A.nearest) { A.id = i; A.nearest = len; A.nrm = nv; A.prim = -1; }
-            }
         }
     }
 }
-// phase 2, per BVH-backed object i: does this ray have to traverse it, and up to which t (exclusive)?
-__device__ __forceinline__ bool bvh_wanted(const SceneDev &S, int i, d3 o, d3 d, const HitAcc &A, double &lim) {
+__device__ __forceinline__ bool is_deferred(const ObjDev &O) { return O.bvh >= 0 || O.kind == OBJ_BEZIER; }
+// phase 2, per deferred object i: does this ray have to visit it, and (meshes) up to which t (exclusive)?
+__device__ __forceinline__ bool deferred_wanted(const SceneDev &S, int i, d3 o, d3 d, const HitAcc &A, double &lim) {
     const ObjDev &O = S.obj[i];
     lim = (A.id > i) ? next_up(A.nearest) : A.nearest;
+    if (O.kind == OBJ_BEZIER) return box_any_face_hit(S.bez[O.aux].box, o, d);  // the first test of Bezier::intersect (bezier.h:226-231)
     if (O.kind == OBJ_PLANE) {  // objects.h:513-517: only when the plane itself is hit, and only lenp < len
         double len = plane_len(O, o, d);
         if (!(len > 0)) return false;
@@ -578,6 +579,26 @@ __device__ __forceinline__ void bvh_merge(const SceneDev &S, int i, int leaf, do
     A.id = i; A.nearest = t; A.nrm = nv; A.prim = B.tri_id[leaf];
 }
 
+// Resolve deferred object i for one ray and merge it into A with the (len, index) order of main.cpp:55-63.
+template <bool COUNT, bool BEZ>
+__device__ __forceinline__ bool deferred_resolve(const SceneDev &S, int i, d3 o, d3 d, double lim, HitAcc &A, TravCounters *tc) {
+    const ObjDev &O = S.obj[i];
+    if (O.kind == OBJ_BEZIER) {
+        if (BEZ) {
+            double len; d3 nv;
+            if (bezier_intersect(S.bez[O.aux], o, d, len, nv) && (len < A.nearest || (len == A.nearest && i < A.id))) {
+                A.id = i; A.nearest = len; A.nrm = nv; A.prim = -1;
+                return true;
+            }
+        }
+        return false;
+    }
+    double t; int leaf;
+    if (!bvh_closest<COUNT>(S.bvh[O.bvh], o, d, lim, t, leaf, tc)) return false;
+    bvh_merge(S, i, leaf, t, A);
+    return true;
+}
+
 // Block-cooperative form (eye pass, parity hooks): every thread of the block must call it.
 template <int BLOCK, bool COUNT>
 __device__ __forceinline__ bool closest_hit_block(const SceneDev &S, bool active, d3 o, d3 d, Hit &h, TraceShared<BLOCK> &sm, TravCounters *tc) {
@@ -587,10 +608,9 @@ __device__ __forceinline__ bool closest_hit_block(const SceneDev &S, bool active
     const int tid = threadIdx.x, lane = tid & 31;
     for (int i = 0; i < S.nobj; i++) {  // uniform control flow: S is uniform
         const ObjDev &O = S.obj[i];
-        if (O.bvh < 0) continue;
-        const BvhDev &B = S.bvh[O.bvh];
+        if (!is_deferred(O)) continue;
         double lim = 0;
-        bool want = active && bvh_wanted(S, i, o, d, A, lim);
+        bool want = active && deferred_wanted(S, i, o, d, A, lim);
         if (tid == 0) sm.count = 0;
         __syncthreads();
         unsigned int mask = __ballot_sync(0xffffffffu, want);
@@ -604,17 +624,22 @@ __device__ __forceinline__ bool closest_hit_block(const SceneDev &S, bool active
             sm.ox[tid] = o.x; sm.oy[tid] = o.y; sm.oz[tid] = o.z;
             sm.dx[tid] = d.x; sm.dy[tid] = d.y; sm.dz[tid] = d.z;
             sm.lim[tid] = lim;
+            sm.near_in[tid] = A.nearest; sm.id_in[tid] = A.id;
         }
         __syncthreads();
         if (tid < (int)sm.count) {
             int s = sm.list[tid];
-            double t; int leaf;
-            bvh_closest<COUNT>(B, mk(sm.ox[s], sm.oy[s], sm.oz[s]), mk(sm.dx[s], sm.dy[s], sm.dz[s]), sm.lim[s], t, leaf, tc);
-            sm.lim[s] = t;
-            sm.leaf[s] = leaf;
+            HitAcc R;
+            R.nearest = sm.near_in[s]; R.id = sm.id_in[s]; R.prim = -1; R.nrm = mk(0, 0, 0);
+            bool hit = deferred_resolve<COUNT, true>(S, i, mk(sm.ox[s], sm.oy[s], sm.oz[s]), mk(sm.dx[s], sm.dy[s], sm.dz[s]), sm.lim[s], R, tc);
+            sm.leaf[s] = hit ? 1 : 0;
+            if (hit) {
+                sm.lim[s] = R.nearest; sm.ox[s] = R.nrm.x; sm.oy[s] = R.nrm.y; sm.oz[s] = R.nrm.z; sm.id_in[s] = R.prim;
+            }
         }
         __syncthreads();
-        if (want && sm.leaf[tid] >= 0) bvh_merge(S, i, sm.leaf[tid], sm.lim[tid], A);
+        if (want && sm.leaf[tid]) { A.id = i; A.nearest = sm.lim[tid]; A.nrm = mk(sm.ox[tid], sm.oy[tid], sm.oz[tid]); A.prim = sm.id_in[tid]; }
+        __syncthreads();  // results are consumed before the next deferred object re-uses the arrays
     }
     h.obj = A.id; h.t = A.nearest; h.n = A.nrm; h.prim = A.prim;
     return A.id >= 0;

@@ -64,7 +64,7 @@ __device__ __forceinline__ void push_ray(const RayQueue &q, unsigned int s, d3 o
 }
 
 struct Counters {
-    unsigned long long eye_segments, photon_segments, diffuse_hits, candidates, deposits;
+    unsigned long long eye_segments, photon_segments, diffuse_hits, candidates, deposits, gathered_hits;
 };
 
 // =================================================================================================================
@@ -320,8 +320,8 @@ __device__ __forceinline__ uint32_t cell_bin(int ix, int iy, int iz) {
 
 // The BVH part of the closest hit for suspended photons: one thread per queue entry, every lane traverses (dense warps,
 // small register footprint). The winner of (analytic hit, mesh hits) is written back into the entry.
-template <bool COUNT>
-__global__ void __launch_bounds__(128, CGRT_TRAV_MINB) photon_traverse_kernel(const __grid_constant__ SceneDev S, PhotonState *__restrict__ q,
+template <bool COUNT, bool BEZ>
+__global__ void __launch_bounds__(128, BEZ ? 1 : CGRT_TRAV_MINB) photon_traverse_kernel(const __grid_constant__ SceneDev S, PhotonState *__restrict__ q,
                                                               const unsigned int *__restrict__ n_in, TravCounters *tcg) {
     const unsigned int total = *n_in;
     TravCounters tcl;
@@ -334,11 +334,10 @@ __global__ void __launch_bounds__(128, CGRT_TRAV_MINB) photon_traverse_kernel(co
         A.nearest = q[i].nearest; A.id = q[i].id; A.prim = -1; A.nrm = mk(0, 0, 0);
         bool changed = false;
         for (int k = 0; k < S.nobj; k++) {
-            if (S.obj[k].bvh < 0) continue;
+            if (!is_deferred(S.obj[k])) continue;
             double lim;
-            if (!bvh_wanted(S, k, o, d, A, lim)) continue;
-            double t; int leaf;
-            if (bvh_closest<COUNT>(S.bvh[S.obj[k].bvh], o, d, lim, t, leaf, &tcl)) { bvh_merge(S, k, leaf, t, A); changed = true; }
+            if (!deferred_wanted(S, k, o, d, A, lim)) continue;
+            changed |= deferred_resolve<COUNT, BEZ>(S, k, o, d, lim, A, &tcl);
         }
         if (changed) {
             q[i].nearest = A.nearest;
@@ -365,8 +364,8 @@ __global__ void __launch_bounds__(128, CGRT_TRAV_MINB) photon_traverse_kernel(co
 // Philox block through the same code (a fresh photon spends two more draws on its position), so refilling adds no divergence.
 enum { PH_NEED = 0, PH_FRESH = 1, PH_DIFFUSE = 2, PH_HAVE_RAY = 3, PH_RESOLVED = 4 };
 
-template <bool FIRST, bool BEZ>
-__global__ void __launch_bounds__(CGRT_TRACE_BLOCK, BEZ ? 1 : CGRT_TRACE_MINB) photon_trace_kernel(const __grid_constant__ SceneDev S, const __grid_constant__ PassParams P,
+template <bool FIRST>
+__global__ void __launch_bounds__(CGRT_TRACE_BLOCK, CGRT_TRACE_MINB) photon_trace_kernel(const __grid_constant__ SceneDev S, const __grid_constant__ PassParams P,
                                                                         uint64_t first_index, unsigned int n, const PhotonState *__restrict__ qin,
                                                                         const unsigned int *__restrict__ n_in, PhotonState *__restrict__ qout,
                                                                         unsigned int *n_out, DepositRec *__restrict__ rec, uint32_t *__restrict__ keys,
@@ -433,10 +432,10 @@ __global__ void __launch_bounds__(CGRT_TRACE_BLOCK, BEZ ? 1 : CGRT_TRACE_MINB) p
         // ---- stage 2: one segment
         bool suspended = false;
         if (!done && mode != PH_RESOLVED) {
-            analytic_phase<BEZ>(S, o, d, A);
+            analytic_phase(S, o, d, A);
             for (int k = 0; k < S.nobj; k++) {
                 double lim;
-                if (S.obj[k].bvh >= 0 && bvh_wanted(S, k, o, d, A, lim)) { suspended = true; break; }
+                if (is_deferred(S.obj[k]) && deferred_wanted(S, k, o, d, A, lim)) { suspended = true; break; }
             }
         }
         {   // suspend in front of a mesh: compact into the next queue (warp ballot + one atomic per warp)
@@ -603,6 +602,7 @@ __global__ void __launch_bounds__(CGRT_DEPOSIT_BLOCK) photon_deposit_kernel(cons
     const int idx = lane / 9, idy = (lane / 3) % 3, idz = lane % 3;  // idx outermost, idz innermost (main.cpp:110-112)
     int qn = 0;
     const size_t n_slots = (size_t)__ldg(n_valid);
+    if (blockIdx.x == 0 && threadIdx.x == 0) atomicAdd(&ctr->gathered_hits, (unsigned long long)n_slots);
     for (size_t span = warp * CGRT_DEPOSIT_SPAN; span < n_slots; span += nwarps * CGRT_DEPOSIT_SPAN) {
         const size_t span_end = span + CGRT_DEPOSIT_SPAN < n_slots ? span + CGRT_DEPOSIT_SPAN : n_slots;
         for (size_t base = span; base < span_end; base += 32) {

@@ -55,6 +55,7 @@ typedef struct cgrt_counters {
     uint64_t node_visits, tri_tests;        /* only filled by cgrt_count_traversal (a counting build of the same traversal) */
     uint64_t hitpoints;                     /* "hitpoints: %d", main.cpp:265 */
     uint64_t gpu_launches;                  /* kernels launched by this ctx so far */
+    uint64_t gathered_hits;                 /* diffuse hits that went through the 27-cell gather (= diffuse_hits unless culling is on) */
 } cgrt_counters;
 
 /* ---- lifecycle ------------------------------------------------------------------------------------------------ */
