@@ -317,3 +317,44 @@ def test_bezier_surface_statistical_parity(gpu, oracle_lib):
     # everything that is not the vase is untouched by the solver: identical
     other = ~on_a & ~on_b
     assert np.array_equal(a["obj"][other], b["obj"][other]) and np.array_equal(a["t"][other], b["t"][other])
+
+
+def test_full_size_properties_c3(gpu):
+    """BASELINE config 3 at its full size (1024x1024, 100,000-triangle glass dragon): size-independent properties.
+    sorted keys + consistent cell table; every photon hit accounted for; shard invariance (two GPUs' index ranges == one range);
+    accepted-photon counts sum to the deposit counter; one more round only shrinks radii; culling changes no accumulator."""
+    s = gpu.preset("c3_dragon_glass")
+    cfg = gpu.RenderConfig(width=1024, height=1024)
+    N = 1 << 21
+    with gpu.Context(0, s, cfg) as g1, gpu.Context(0, s, cfg) as g2:
+        for g in (g1, g2):
+            g.eye_pass(); g.build_grid()
+        hp = g1.download_hitpoints()
+        n = len(hp["key"])
+        assert n > 1024 * 1024 and g1.counters()["eye_segments"] >= n
+        assert np.all(np.diff(hp["key"].astype(np.int64)) >= 0)                       # sorted by bucket key
+        same = np.diff(hp["key"].astype(np.int64)) == 0
+        assert np.all(np.diff(hp["seq"].astype(np.int64))[same] > 0)                  # creation order inside a bucket
+        cs = g1.download_grid().astype(np.int64)
+        assert cs[0] == 0 and cs[-1] == n and np.array_equal(np.diff(cs), np.bincount(hp["key"], minlength=cfg.hashsize))
+        k, _ = g1.hash_keys(hp["pos"], cfg.hashsize, 200.0 / cfg.height)
+        assert np.array_equal(k, hp["key"])                                           # keys are the hash of the stored positions
+        # one range vs two disjoint ranges (what two GPUs trace), culling on vs off
+        g2.set_culling(False)
+        g1.photon_pass(0, N)
+        g2.photon_pass(N // 2, N - N // 2); g2.photon_pass(0, N // 2)
+        d1, m1 = g1.download_accum(); d2, m2 = g2.download_accum()
+        assert np.array_equal(m1, m2)
+        assert np.allclose(d1, d2, rtol=1e-9, atol=1e-9)
+        c1, c2 = g1.counters(), g2.counters()
+        assert c1["deposits"] == c2["deposits"] == int(m1.sum()) > N
+        assert c1["photon_segments"] == c2["photon_segments"] and c1["diffuse_hits"] == c2["diffuse_hits"]
+        assert c1["photon_segments"] <= 5 * N and c1["diffuse_hits"] <= c1["photon_segments"]
+        assert c1["gathered_hits"] <= c1["diffuse_hits"] == c2["gathered_hits"] and c1["candidates"] <= c2["candidates"]
+        g1.round_update()
+        hp2 = g1.download_hitpoints()
+        assert np.array_equal(hp2["n"], m1.astype(np.int32))
+        assert np.all(hp2["r2"] <= hp["r2"]) and np.all(hp2["r2"][m1 > 0] < hp["r2"][m1 > 0])
+        assert np.all(hp2["flux"] >= 0) and np.isfinite(hp2["flux"]).all()
+        img = g1.gather_image(float(N))
+        assert np.isfinite(img).all() and img.min() >= 0 and img.mean() > 0.01
