@@ -6,6 +6,7 @@
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
+#include <mutex>
 #include <string>
 #include <vector>
 
@@ -36,6 +37,43 @@ struct BvhBuild {
     double *tri9 = nullptr;  // original order, device
     int ntris = 0;
 };
+
+// Process-wide cache of the photon pass's large buffers (deposit tables 2 x 8.4 GB, suspended-photon queues 2 x 2.1 GB at 16 Mi
+// photons per launch). A render() creates and destroys a context; handing 20 GB back to the stream-ordered pool and carving it up
+// again for the next context was measured to cost up to 0.4 s per render. Blocks parked here are plain cudaMalloc allocations that
+// the next context of the same device takes over as they are; they are only freed at process exit.
+struct ArenaBlock {
+    int device;
+    size_t bytes;
+    void *ptr;
+};
+std::mutex g_arena_mutex;
+std::vector<ArenaBlock> g_arena;
+
+void *arena_take(int device, size_t bytes) {
+    {
+        std::lock_guard<std::mutex> lk(g_arena_mutex);
+        size_t best = g_arena.size();
+        for (size_t i = 0; i < g_arena.size(); i++)
+            if (g_arena[i].device == device && g_arena[i].bytes >= bytes && (best == g_arena.size() || g_arena[i].bytes < g_arena[best].bytes)) best = i;
+        if (best != g_arena.size() && g_arena[best].bytes <= bytes + bytes / 4 + (1u << 20)) {  // close fit only
+            void *p = g_arena[best].ptr;
+            g_arena.erase(g_arena.begin() + (long)best);
+            return p;
+        }
+    }
+    void *p = nullptr;
+    if (cudaMalloc(&p, bytes) != cudaSuccess) { cudaGetLastError(); return nullptr; }
+    return p;
+}
+void arena_give(int device, size_t bytes, void *p) {
+    if (!p) return;
+    std::lock_guard<std::mutex> lk(g_arena_mutex);
+    size_t held = 0;
+    for (const ArenaBlock &b : g_arena) held += b.device == device ? b.bytes : 0;
+    if (held + bytes > ((size_t)48 << 30)) { cudaFree(p); return; }  // park at most 48 GB per device
+    g_arena.push_back(ArenaBlock{device, bytes, p});
+}
 
 // ping-pong buffers of the radix sort
 template <typename K>
@@ -336,10 +374,15 @@ int ensure_photon_buffers(cgrt_ctx *ctx, size_t photons, size_t slots) {
         CK(cudaStreamSynchronize(ctx->tstream));
         CK(cudaStreamSynchronize(ctx->stream));
         for (auto &b : ctx->dep) {
-            if (ctx->dep_cap) { CKS(dfree(ctx, b.rec)); CKS(dfree(ctx, b.keys)); CKS(dfree(ctx, b.perm)); }
-            CKS(dalloc(ctx, &b.rec, slots));
-            CKS(dalloc(ctx, &b.keys, slots));
-            CKS(dalloc(ctx, &b.perm, slots));
+            if (ctx->dep_cap) {
+                arena_give(ctx->device, ctx->dep_cap * sizeof(DepositRec), b.rec);
+                arena_give(ctx->device, ctx->dep_cap * sizeof(uint32_t), b.keys);
+                arena_give(ctx->device, ctx->dep_cap * sizeof(uint32_t), b.perm);
+            }
+            b.rec = (DepositRec *)arena_take(ctx->device, slots * sizeof(DepositRec));
+            b.keys = (uint32_t *)arena_take(ctx->device, slots * sizeof(uint32_t));
+            b.perm = (uint32_t *)arena_take(ctx->device, slots * sizeof(uint32_t));
+            if (!b.rec || !b.keys || !b.perm) FAIL(CGRT_ERR_CUDA, "out of device memory for the deposit tables");
             b.drained_valid = false;
         }
         ctx->dep_cap = slots;
@@ -347,9 +390,11 @@ int ensure_photon_buffers(cgrt_ctx *ctx, size_t photons, size_t slots) {
     }
     if (photons > ctx->pq_cap) {
         CK(cudaStreamSynchronize(ctx->tstream));
-        if (ctx->pq_cap) { CKS(dfree(ctx, ctx->pq[0])); CKS(dfree(ctx, ctx->pq[1])); }
-        CKS(dalloc(ctx, &ctx->pq[0], photons));
-        CKS(dalloc(ctx, &ctx->pq[1], photons));
+        for (int k = 0; k < 2; k++) {
+            if (ctx->pq_cap) arena_give(ctx->device, ctx->pq_cap * sizeof(PhotonState), ctx->pq[k]);
+            ctx->pq[k] = (PhotonState *)arena_take(ctx->device, photons * sizeof(PhotonState));
+            if (!ctx->pq[k]) FAIL(CGRT_ERR_CUDA, "out of device memory for the photon queues");
+        }
         ctx->pq_cap = photons;
         fresh = true;
     }
@@ -491,7 +536,11 @@ int cgrt_destroy(cgrt_ctx *ctx) {
     for (auto &b : ctx->dep) {
         if (b.traced) cudaEventDestroy(b.traced);
         if (b.drained) cudaEventDestroy(b.drained);
+        arena_give(ctx->device, ctx->dep_cap * sizeof(DepositRec), b.rec);
+        arena_give(ctx->device, ctx->dep_cap * sizeof(uint32_t), b.keys);
+        arena_give(ctx->device, ctx->dep_cap * sizeof(uint32_t), b.perm);
     }
+    for (int k = 0; k < 2; k++) arena_give(ctx->device, ctx->pq_cap * sizeof(PhotonState), ctx->pq[k]);
     for (void *p : ctx->allocs) cudaFreeAsync(p, ctx->stream);
     cudaStreamSynchronize(ctx->stream);
     if (ctx->ev[0]) cudaEventDestroy(ctx->ev[0]);
