@@ -647,8 +647,14 @@ __global__ void __launch_bounds__(CGRT_DEPOSIT_BLOCK) photon_deposit_kernel(cons
                 const uint32_t excl = incl - cnt;
                 const uint32_t total = __shfl_sync(0xffffffffu, incl, 31);
                 cand_total += (lane == 0) ? (unsigned long long)total * (unsigned int)__popc(grp) : 0ull;
+                // the cell of this group as a float box (a hair larger): a candidate whose sphere does not reach the box cannot accept
+                // any hit of the group and is dropped once per group instead of being tested against every hit
+                const float bx0 = (float)(-35.0 + (double)cx * P.celllength), by0 = (float)(-35.0 + (double)cy * P.celllength),
+                            bz0 = (float)(-15.0 + (double)cz * P.celllength), bw = (float)P.celllength;
+                const float bm = 1e-5f * (fabsf(bx0) + fabsf(by0) + fabsf(bz0) + bw + 1.0f);
                 for (uint32_t c0 = 0; c0 < total; c0 += 64) {
                     // ---- stage up to 64 candidates of the concatenated bucket lists
+                    int nc = 0;
 #pragma unroll
                     for (int h = 0; h < 2; h++) {
                         const uint32_t c = c0 + 32 * h + lane;
@@ -661,17 +667,27 @@ __global__ void __launch_bounds__(CGRT_DEPOSIT_BLOCK) photon_deposit_kernel(cons
                         }
                         const uint32_t e_lo = __shfl_sync(0xffffffffu, excl, lo);
                         const uint32_t b_lo = __shfl_sync(0xffffffffu, beg, lo);
+                        bool keep = false;
+                        uint32_t hidx = 0;
+                        float4 q = make_float4(0.f, 0.f, 0.f, -1.f);
                         if (c < total) {
-                            const uint32_t hidx = b_lo + (c - e_lo);
-                            cpre[32 * h + lane] = __ldg(pre + hidx);
-                            cidx[32 * h + lane] = hidx;
-                        } else {
-                            cpre[32 * h + lane] = make_float4(0.f, 0.f, 0.f, -1.f);  // never passes
+                            hidx = b_lo + (c - e_lo);
+                            q = __ldg(pre + hidx);
+                            const float ex = fmaxf(fmaxf(bx0 - bm - q.x, q.x - (bx0 + bw + bm)), 0.f);
+                            const float ey = fmaxf(fmaxf(by0 - bm - q.y, q.y - (by0 + bw + bm)), 0.f);
+                            const float ez = fmaxf(fmaxf(bz0 - bm - q.z, q.z - (bz0 + bw + bm)), 0.f);
+                            keep = fmaf(ez, ez, fmaf(ey, ey, ex * ex)) <= q.w;
                         }
+                        const unsigned int km = __ballot_sync(0xffffffffu, keep);
+                        if (keep) {
+                            const int at = nc + __popc(km & lt);
+                            cpre[at] = q;
+                            cidx[at] = hidx;
+                        }
+                        nc += __popc(km);
                     }
                     __syncwarp();
                     // ---- prefilter: every lane tests its own hit against the staged candidates (shared-memory broadcast)
-                    const int nc = (int)(total - c0 < 64u ? total - c0 : 64u);
                     unsigned int m_lo = 0, m_hi = 0;
 #pragma unroll 8
                     for (int k = 0; k < 32; k++) {
