@@ -187,6 +187,7 @@ def run_gpu(args):
     # ---- setup (untimed for `value`): scene upload + LBVH build, tile-sharded eye pass + all-gather, grid
     g = Context(local)
     g.set_config(cfg, accum_mode=args.accum)
+    g.set_overlap(bool(args.overlap))
     scene.build_into(g)
     t0 = time.time()
     g.commit()
@@ -335,6 +336,7 @@ def main():
     ap.add_argument("--workload", default=WORKLOAD, choices=sorted(WORKLOADS), help="BASELINE.json config (default: the headline config c3)")
     ap.add_argument("--photons", type=int, default=0, help="photons per GPU per step (default: the workload's photons per round; c3 = 16 Mi)")
     ap.add_argument("--accum", type=int, default=1, help="0: fp64 atomics, 1: one v4.f32 red per deposit (SURVEY 8e: float32 x4 accumulators)")
+    ap.add_argument("--overlap", type=int, default=0, help="1: trace of round r+1 overlaps the deposit of round r on a second stream")
     ap.add_argument("--cpu-photons", type=int, default=400000, help="photon budget of the CPU baseline sample (0 = skip)")
     ap.add_argument("--ref-photons", type=int, default=200000, help="photons per step of --impl reference")
     ap.add_argument("--e2e-rounds", type=int, default=-1, help="rounds of the end-to-end render() (default: the workload's own, c3 = 50; 0 = skip)")

@@ -130,9 +130,10 @@ struct cgrt_ctx {
     size_t dep_cap = 0;          // deposit slots per buffer
     unsigned int chunk_seq = 0;
     cudaStream_t tstream = nullptr;
-    int overlap = 1;
+    int overlap = 0;  // measured on c3: the two halves slow each other down by more than they overlap (25.3 vs 24.2 ms per round)
     // resident-grid sizes of the persistent photon kernels (SMs x occupancy), so that static striding leaves no tail of late blocks
-    unsigned int grid_first = 592, grid_cont = 592;
+    unsigned int grid_first = 592, grid_cont = 592, trav_grid = 0;
+    std::vector<cudaEvent_t> timeline;  // dev: CGRT_TIMELINE=1 records (trace begin, trace end, deposit begin, deposit end) per chunk
     PhotonState *pq[2] = {nullptr, nullptr};
     size_t pq_cap = 0;
     uint32_t *reach = nullptr;        // reach bitmap (cells within 2 cells of a hitpoint), built with the grid
@@ -495,6 +496,9 @@ int cgrt_create(int device, cgrt_ctx **out) {
         auto occ = [&](const void *k) { return (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, k, CGRT_TRACE_BLOCK, 0) == cudaSuccess && nb > 0) ? (unsigned int)(nb * sms) : 592u; };
         ctx->grid_first = occ((const void *)photon_trace_kernel<true>);
         ctx->grid_cont = occ((const void *)photon_trace_kernel<false>);
+        // resident blocks per SM of the two pipelined halves (dev knobs: how the trace and the deposit stream share an SM)
+        if (const char *e = getenv("CGRT_TRACE_BPS")) { unsigned int b = (unsigned int)atoi(e) * (unsigned int)sms; if (b) { ctx->grid_first = b; ctx->grid_cont = b; ctx->trav_grid = b; } }
+        if (const char *e = getenv("CGRT_DEPOSIT_BPS")) { unsigned int b = (unsigned int)atoi(e) * (unsigned int)sms; if (b) ctx->deposit_grid = b; }
         cudaGetLastError();
     }
     cgrt_default_config(&ctx->cfg);
@@ -574,6 +578,15 @@ int cgrt_synchronize(cgrt_ctx *ctx) {
     if (!ctx) return CGRT_ERR_INVALID;
     CK(cudaStreamSynchronize(ctx->tstream));
     CK(cudaStreamSynchronize(ctx->stream));
+    if (!ctx->timeline.empty()) {
+        for (size_t k = 0; k + 3 < ctx->timeline.size(); k += 4) {
+            float t[4];
+            for (int j = 0; j < 4; j++) cudaEventElapsedTime(&t[j], ctx->timeline[0], ctx->timeline[k + j]);
+            fprintf(stderr, "[cgrt timeline] chunk %zu: trace %8.2f .. %8.2f ms   deposit %8.2f .. %8.2f ms\n", k / 4, t[0], t[1], t[2], t[3]);
+        }
+        for (cudaEvent_t ev : ctx->timeline) cudaEventDestroy(ev);
+        ctx->timeline.clear();
+    }
     return CGRT_OK;
 }
 
@@ -997,7 +1010,7 @@ int cgrt_photon_pass(cgrt_ctx *ctx, uint64_t first, uint64_t count) {
     if (first_chunk == 0) return CGRT_OK;
     CKS(ensure_photon_buffers(ctx, first_chunk, first_chunk * (size_t)P.max_depth));
     std::vector<cudaEvent_t> evs;
-    const unsigned int resume_grid = ctx->deposit_grid;  // 8 resident blocks per SM, grid-stride over the queue
+    const unsigned int resume_grid = ctx->trav_grid ? ctx->trav_grid : 148u * 8u;  // 8 resident blocks per SM, grid-stride over the queue
     const bool overlap = ctx->overlap && !ctx->profiling;
     cudaStream_t D = ctx->stream, T = overlap ? ctx->tstream : ctx->stream;
     for (uint64_t done = 0; done < count; done += chunk) {
@@ -1012,6 +1025,9 @@ int cgrt_photon_pass(cgrt_ctx *ctx, uint64_t first, uint64_t count) {
         }
         // ---- trace (stream T): may not overwrite the buffer before its previous deposit pass has drained it
         if (B.drained_valid) CK(cudaStreamWaitEvent(T, B.drained, 0));
+        static const bool timeline_on = getenv("CGRT_TIMELINE") != nullptr;
+        auto mark = [&](cudaStream_t st) { if (timeline_on) { cudaEvent_t ev; cudaEventCreate(&ev); cudaEventRecord(ev, st); ctx->timeline.push_back(ev); } };
+        mark(T);
         CK(cudaMemsetAsync(B.keys, 0xff, slots * sizeof(uint32_t), T));
         CK(cudaMemsetAsync(B.hist, 0, (size_t)CGRT_NBINS * sizeof(uint32_t), T));
         CK(cudaMemsetAsync(ctx->d_qcount + 2, 0, 6 * sizeof(unsigned int), T));
@@ -1042,11 +1058,13 @@ int cgrt_photon_pass(cgrt_ctx *ctx, uint64_t first, uint64_t count) {
         }
 #undef LAUNCH_PT
         if (ctx->profiling) CK(cudaEventRecord(e[1], D));
+        mark(T);
         // ---- sort + deposit (stream D) after the trace of this buffer
         if (overlap) {
             CK(cudaEventRecord(B.traced, T));
             CK(cudaStreamWaitEvent(D, B.traced, 0));
         }
+        mark(D);
         if (ctx->nhp > 0) {
             const int nsb = (int)(CGRT_NBINS / (CGRT_SCAN_BLOCK * CGRT_SCAN_ITEMS));
             bin_scan_blocks_kernel<<<nsb, CGRT_SCAN_BLOCK, 0, D>>>(B.hist, B.bsum);
@@ -1067,6 +1085,7 @@ int cgrt_photon_pass(cgrt_ctx *ctx, uint64_t first, uint64_t count) {
         } else if (ctx->profiling) {
             CK(cudaEventRecord(e[2], D));
         }
+        mark(D);
         if (overlap) {
             CK(cudaEventRecord(B.drained, D));
             B.drained_valid = true;

@@ -142,9 +142,10 @@ int cgrt_get_counters(cgrt_ctx *ctx, cgrt_counters *out);
 /* on != 0: the photon trace kernels run their counting build (same traversal + node-visit / triangle-test counters,
  * reported by cgrt_get_counters). Used outside timed regions to derive the algorithmic bytes of the roofline. */
 int cgrt_set_counting(cgrt_ctx *ctx, int on);
-/* on != 0 (default): cgrt_photon_pass traces on a second internal stream into double-buffered deposit tables, so the trace of one
- * chunk (or of the next round) overlaps the sort + deposit of the previous one. Everything a caller can observe stays ordered on
- * the stream cgrt_get_stream returns. Profiling forces it off for the profiled passes. */
+/* on != 0: cgrt_photon_pass traces on a second internal stream into double-buffered deposit tables, so the trace of one chunk (or
+ * of the next round) overlaps the sort + deposit of the previous one. Everything a caller can observe stays ordered on the stream
+ * cgrt_get_stream returns. Off by default: on one B200 both halves are bound by the same SM issue slots and registers and slow each
+ * other down by more than they overlap (25.3 vs 24.2 ms per 16 Mi-photon round); it pays when a slow collective sits between rounds. */
 int cgrt_set_overlap(cgrt_ctx *ctx, int on);
 /* on != 0 (default): photon hits whose cell is farther than 2 cells from every hitpoint are dropped before the gather — they
  * cannot pass the distance test of main.cpp:116 — and are not counted in counters.candidates. Deposits, accepted-photon
