@@ -126,8 +126,8 @@ struct cgrt_ctx {
         uint32_t *nvalid = nullptr;
         cudaEvent_t traced = nullptr, drained = nullptr;
         bool drained_valid = false;
+        size_t cap = 0;               // slots
     } dep[2];
-    size_t dep_cap = 0;          // deposit slots per buffer
     unsigned int chunk_seq = 0;
     cudaStream_t tstream = nullptr;
     int overlap = 0;  // measured on c3: the two halves slow each other down by more than they overlap (25.3 vs 24.2 ms per round)
@@ -371,22 +371,23 @@ int ensure_queues(cgrt_ctx *ctx, size_t cap) {
 }
 int ensure_photon_buffers(cgrt_ctx *ctx, size_t photons, size_t slots) {
     bool fresh = false;
-    if (slots > ctx->dep_cap) {
+    const int nbuf = ctx->overlap ? 2 : 1;  // the second deposit table only exists while the two-stream pipeline is on
+    for (int bi = 0; bi < nbuf; bi++) {
+        auto &b = ctx->dep[bi];
+        if (slots <= b.cap) continue;
         CK(cudaStreamSynchronize(ctx->tstream));
         CK(cudaStreamSynchronize(ctx->stream));
-        for (auto &b : ctx->dep) {
-            if (ctx->dep_cap) {
-                arena_give(ctx->device, ctx->dep_cap * sizeof(DepositRec), b.rec);
-                arena_give(ctx->device, ctx->dep_cap * sizeof(uint32_t), b.keys);
-                arena_give(ctx->device, ctx->dep_cap * sizeof(uint32_t), b.perm);
-            }
-            b.rec = (DepositRec *)arena_take(ctx->device, slots * sizeof(DepositRec));
-            b.keys = (uint32_t *)arena_take(ctx->device, slots * sizeof(uint32_t));
-            b.perm = (uint32_t *)arena_take(ctx->device, slots * sizeof(uint32_t));
-            if (!b.rec || !b.keys || !b.perm) FAIL(CGRT_ERR_CUDA, "out of device memory for the deposit tables");
-            b.drained_valid = false;
+        if (b.cap) {
+            arena_give(ctx->device, b.cap * sizeof(DepositRec), b.rec);
+            arena_give(ctx->device, b.cap * sizeof(uint32_t), b.keys);
+            arena_give(ctx->device, b.cap * sizeof(uint32_t), b.perm);
         }
-        ctx->dep_cap = slots;
+        b.rec = (DepositRec *)arena_take(ctx->device, slots * sizeof(DepositRec));
+        b.keys = (uint32_t *)arena_take(ctx->device, slots * sizeof(uint32_t));
+        b.perm = (uint32_t *)arena_take(ctx->device, slots * sizeof(uint32_t));
+        if (!b.rec || !b.keys || !b.perm) FAIL(CGRT_ERR_CUDA, "out of device memory for the deposit tables");
+        b.cap = slots;
+        b.drained_valid = false;
         fresh = true;
     }
     if (photons > ctx->pq_cap) {
@@ -496,6 +497,7 @@ int cgrt_create(int device, cgrt_ctx **out) {
         auto occ = [&](const void *k) { return (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, k, CGRT_TRACE_BLOCK, 0) == cudaSuccess && nb > 0) ? (unsigned int)(nb * sms) : 592u; };
         ctx->grid_first = occ((const void *)photon_trace_kernel<true>);
         ctx->grid_cont = occ((const void *)photon_trace_kernel<false>);
+        if (const char *e = getenv("CGRT_PHOTON_CHUNK")) { long long c = atoll(e); if (c > 0) ctx->photon_chunk = (size_t)c; }  // tests: force multi-chunk passes
         // resident blocks per SM of the two pipelined halves (dev knobs: how the trace and the deposit stream share an SM)
         if (const char *e = getenv("CGRT_TRACE_BPS")) { unsigned int b = (unsigned int)atoi(e) * (unsigned int)sms; if (b) { ctx->grid_first = b; ctx->grid_cont = b; ctx->trav_grid = b; } }
         if (const char *e = getenv("CGRT_DEPOSIT_BPS")) { unsigned int b = (unsigned int)atoi(e) * (unsigned int)sms; if (b) ctx->deposit_grid = b; }
@@ -540,9 +542,11 @@ int cgrt_destroy(cgrt_ctx *ctx) {
     for (auto &b : ctx->dep) {
         if (b.traced) cudaEventDestroy(b.traced);
         if (b.drained) cudaEventDestroy(b.drained);
-        arena_give(ctx->device, ctx->dep_cap * sizeof(DepositRec), b.rec);
-        arena_give(ctx->device, ctx->dep_cap * sizeof(uint32_t), b.keys);
-        arena_give(ctx->device, ctx->dep_cap * sizeof(uint32_t), b.perm);
+        if (b.cap) {
+            arena_give(ctx->device, b.cap * sizeof(DepositRec), b.rec);
+            arena_give(ctx->device, b.cap * sizeof(uint32_t), b.keys);
+            arena_give(ctx->device, b.cap * sizeof(uint32_t), b.perm);
+        }
     }
     for (int k = 0; k < 2; k++) arena_give(ctx->device, ctx->pq_cap * sizeof(PhotonState), ctx->pq[k]);
     for (void *p : ctx->allocs) cudaFreeAsync(p, ctx->stream);
@@ -1017,7 +1021,7 @@ int cgrt_photon_pass(cgrt_ctx *ctx, uint64_t first, uint64_t count) {
         const size_t n = (size_t)((count - done) < chunk ? (count - done) : chunk);
         const uint64_t base = first + done;
         const size_t slots = n * (size_t)P.max_depth;
-        cgrt_ctx::DepBuf &B = ctx->dep[ctx->chunk_seq++ & 1u];
+        cgrt_ctx::DepBuf &B = ctx->dep[overlap ? (ctx->chunk_seq++ & 1u) : 0u];
         cudaEvent_t e[4] = {nullptr, nullptr, nullptr, nullptr};
         if (ctx->profiling) {
             for (int k = 0; k < 4; k++) { CK(cudaEventCreate(&e[k])); evs.push_back(e[k]); }

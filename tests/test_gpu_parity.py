@@ -358,3 +358,25 @@ def test_full_size_properties_c3(gpu):
         assert np.all(hp2["flux"] >= 0) and np.isfinite(hp2["flux"]).all()
         img = g1.gather_image(float(N))
         assert np.isfinite(img).all() and img.min() >= 0 and img.mean() > 0.01
+
+
+@pytest.mark.parametrize("overlap", [0, 1])
+def test_chunked_and_pipelined_photon_pass(gpu, oracle_lib, overlap, monkeypatch):
+    """A pass split into many chunks (and, with overlap on, pipelined over two streams with double-buffered deposit tables) leaves
+    exactly the accumulators of the oracle's single loop."""
+    monkeypatch.setenv("CGRT_PHOTON_CHUNK", "7001")
+    s = gpu.preset("c2_bunny_chess")
+    cfg = gpu.RenderConfig(width=128, height=96)
+    o = oracle_lib.Oracle(s, cfg)
+    o.eye_pass()
+    with gpu.Context(0, s, cfg) as g:
+        g.set_overlap(bool(overlap))
+        g.eye_pass(); g.build_grid()
+        for r in range(3):
+            g.photon_pass(r * 30000, 30000); o.photon_pass(r * 30000, 30000)
+            df, m = g.download_accum(); odf, om = o.download_accum()
+            assert np.array_equal(m.astype(np.int64), om.astype(np.int64))
+            assert np.allclose(df, odf, rtol=1e-9, atol=1e-12)
+            g.round_update(); o.round_update()
+        assert np.allclose(g.gather_image(90000.0), o.gather_image(90000.0), rtol=1e-9, atol=1e-12)
+        assert g.counters()["gpu_launches"] > 3 * 5 * 12
