@@ -292,7 +292,8 @@ class Context:
         self._ck(self.L.cgrt_set_profiling(self.h, int(on)))
 
     def timings(self):
-        ms = (C.c_double * 8)()
+        ms = (C.c_double * 12)()
         self._ck(self.L.cgrt_get_timings(self.h, ms))
-        names = ["eye", "grid", "photon_trace", "photon_deposit", "update", "gather", "deposit_sort", "r7"]
+        names = ["eye", "grid", "photon_trace", "photon_deposit", "update", "gather", "deposit_sort", "trace_traverse", "trace_continue",
+                 "trace_emit", "r10", "r11"]
         return {n: ms[i] for i, n in enumerate(names)}

@@ -8,6 +8,7 @@
 #include <cstring>
 #include <mutex>
 #include <string>
+#include <utility>
 #include <vector>
 
 #include "cgrt_passes.cuh"
@@ -133,6 +134,7 @@ struct cgrt_ctx {
     int overlap = 0;  // measured on c3: the two halves slow each other down by more than they overlap (25.3 vs 24.2 ms per round)
     // resident-grid sizes of the persistent photon kernels (SMs x occupancy), so that static striding leaves no tail of late blocks
     unsigned int grid_first = 592, grid_cont = 592, trav_grid = 0;
+    std::vector<std::pair<cudaEvent_t, int>> prof_marks;
     std::vector<cudaEvent_t> timeline;  // dev: CGRT_TIMELINE=1 records (trace begin, trace end, deposit begin, deposit end) per chunk
     PhotonState *pq[2] = {nullptr, nullptr};
     size_t pq_cap = 0;
@@ -143,7 +145,7 @@ struct cgrt_ctx {
     uint64_t launches = 0;
     unsigned int deposit_grid = 148 * 8;  // resident deposit blocks: 8 x 256 threads per SM
     int profiling = 0;   // 1: time every photon kernel with events (serialises host and device at the end of each pass)
-    double ms[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+    double ms[12] = {0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0};
     cudaEvent_t ev[2] = {nullptr, nullptr};
     size_t photon_chunk = 16u << 20;  // photons per trace launch: bounds the deposit table (chunk * max_depth * 100 B)
     int counting = 0;  // 1: photon trace kernels also count BVH node visits / triangle tests (roofline accounting)
@@ -1023,6 +1025,14 @@ int cgrt_photon_pass(cgrt_ctx *ctx, uint64_t first, uint64_t count) {
         const size_t slots = n * (size_t)P.max_depth;
         cgrt_ctx::DepBuf &B = ctx->dep[overlap ? (ctx->chunk_seq++ & 1u) : 0u];
         cudaEvent_t e[4] = {nullptr, nullptr, nullptr, nullptr};
+        std::vector<std::pair<cudaEvent_t, int>> marks;  // profiling: (event after a launch, timing slot of that launch)
+        auto stamp = [&](int slot) {
+            if (!ctx->profiling) return;
+            cudaEvent_t ev;
+            cudaEventCreate(&ev);
+            cudaEventRecord(ev, D);
+            marks.push_back(std::make_pair(ev, slot));
+        };
         if (ctx->profiling) {
             for (int k = 0; k < 4; k++) { CK(cudaEventCreate(&e[k])); evs.push_back(e[k]); }
             CK(cudaEventRecord(e[0], D));
@@ -1041,7 +1051,9 @@ int cgrt_photon_pass(cgrt_ctx *ctx, uint64_t first, uint64_t count) {
                                                              ctx->cull ? ctx->reach : nullptr, ctx->d_ctr)
         {
             unsigned int want = nblk(n, CGRT_TRACE_BLOCK);
+            stamp(-1);
             LAUNCH_PT(true, (want < ctx->grid_first ? want : ctx->grid_first), nullptr, nullptr, ctx->pq[0], qc);
+            stamp(9);
         }
         ctx->launches++;
         if (ctx->S.nbvh > 0 || ctx->S.nbez > 0) {
@@ -1056,7 +1068,9 @@ int cgrt_photon_pass(cgrt_ctx *ctx, uint64_t first, uint64_t count) {
                     if (ctx->counting) photon_traverse_kernel<true, false><<<resume_grid, 128, 0, T>>>(ctx->S, qin, nin, ctx->d_tc);
                     else photon_traverse_kernel<false, false><<<resume_grid, 128, 0, T>>>(ctx->S, qin, nin, ctx->d_tc);
                 }
+                stamp(7);
                 LAUNCH_PT(false, ctx->grid_cont, qin, nin, qout, qc + pass);
+                stamp(8);
                 ctx->launches += 2;
             }
         }
@@ -1095,6 +1109,7 @@ int cgrt_photon_pass(cgrt_ctx *ctx, uint64_t first, uint64_t count) {
             B.drained_valid = true;
         }
         if (ctx->profiling) CK(cudaEventRecord(e[3], D));
+        for (auto &m : marks) ctx->prof_marks.push_back(m);
         CK(cudaGetLastError());
     }
     if (ctx->profiling) {
@@ -1109,6 +1124,14 @@ int cgrt_photon_pass(cgrt_ctx *ctx, uint64_t first, uint64_t count) {
             ctx->ms[3] += t23;
         }
         for (cudaEvent_t ev : evs) cudaEventDestroy(ev);
+        for (size_t k = 1; k < ctx->prof_marks.size(); k++) {
+            if (ctx->prof_marks[k].second < 0) continue;  // -1 opens a chunk
+            float t = 0;
+            cudaEventElapsedTime(&t, ctx->prof_marks[k - 1].first, ctx->prof_marks[k].first);
+            ctx->ms[ctx->prof_marks[k].second] += t;
+        }
+        for (auto &m : ctx->prof_marks) cudaEventDestroy(m.first);
+        ctx->prof_marks.clear();
     }
     return CGRT_OK;
 }
@@ -1293,9 +1316,9 @@ int cgrt_set_profiling(cgrt_ctx *ctx, int on) {
     return CGRT_OK;
 }
 
-int cgrt_get_timings(cgrt_ctx *ctx, double ms[8]) {
+int cgrt_get_timings(cgrt_ctx *ctx, double ms[12]) {
     if (!ctx || !ms) return CGRT_ERR_INVALID;
-    for (int i = 0; i < 8; i++) ms[i] = ctx->ms[i];
+    for (int i = 0; i < 12; i++) ms[i] = ctx->ms[i];
     return CGRT_OK;
 }
 

@@ -154,9 +154,11 @@ int cgrt_set_culling(cgrt_ctx *ctx, int on);
 /* on != 0: every photon kernel launch is bracketed by CUDA events on the ctx stream and cgrt_photon_pass ends with a
  * synchronise (per-kernel durations for the roofline). Off (default): cgrt_photon_pass is asynchronous. */
 int cgrt_set_profiling(cgrt_ctx *ctx, int on);
-/* Accumulated device time per phase on the ctx stream (CUDA events), milliseconds: [0] eye, [1] grid, [2] photon trace kernels,
- * [3] photon deposit kernel, [6] deposit-key radix sort ([2],[3],[6] only while profiling is on), [4] update, [5] gather. */
-int cgrt_get_timings(cgrt_ctx *ctx, double ms[8]);
+/* Accumulated device time per phase on the ctx stream (CUDA events), milliseconds: [0] eye, [1] grid, [2] all photon trace launches,
+ * [3] photon_deposit_kernel, [4] round update, [5] image gather, [6] deposit counting sort, and the split of [2]:
+ * [9] photon_trace_kernel<emission>, [7] photon_traverse_kernel launches, [8] photon_trace_kernel<continuation> launches.
+ * [2],[3],[6]-[9] are only filled while profiling is on. */
+int cgrt_get_timings(cgrt_ctx *ctx, double ms[12]);
 
 #ifdef __cplusplus
 }
