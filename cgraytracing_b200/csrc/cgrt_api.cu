@@ -113,7 +113,7 @@ struct cgrt_ctx {
 
     // queues
     RayQueue q[2];       // eye pass only: the photon pass keeps its rays in registers
-    unsigned int q_cap = 0;
+    size_t q_cap[2] = {0, 0};
     unsigned int *d_qcount = nullptr;  // [0],[1]: eye ray queues; [2..7]: suspended-photon queues of the photon pass
     // photon pass buffers
     // Deposit tables are double-buffered: the trace kernels of chunk k+1 (stream `tstream`) run while the sort + deposit kernels of
@@ -363,12 +363,12 @@ int free_queue(cgrt_ctx *ctx, RayQueue &q) {
     memset(&q, 0, sizeof q);
     return 0;
 }
-int ensure_queues(cgrt_ctx *ctx, size_t cap) {
-    if (cap <= ctx->q_cap) return 0;
-    if (ctx->q_cap) { CKS(free_queue(ctx, ctx->q[0])); CKS(free_queue(ctx, ctx->q[1])); }
-    CKS(alloc_queue(ctx, ctx->q[0], cap, true));
-    CKS(alloc_queue(ctx, ctx->q[1], cap, true));
-    ctx->q_cap = (unsigned int)cap;
+// Only the OUTPUT queue of a bounce may be (re)allocated: the input queue holds the live rays of the current wavefront.
+int ensure_queue(cgrt_ctx *ctx, int which, size_t cap) {
+    if (cap <= ctx->q_cap[which]) return 0;
+    if (ctx->q_cap[which]) CKS(free_queue(ctx, ctx->q[which]));
+    CKS(alloc_queue(ctx, ctx->q[which], cap, true));
+    ctx->q_cap[which] = cap;
     return 0;
 }
 int ensure_photon_buffers(cgrt_ctx *ctx, size_t photons, size_t slots) {
@@ -877,6 +877,7 @@ int cgrt_eye_pass(cgrt_ctx *ctx, int y0, int y1) {
     PhaseTimer timer(ctx, 0);
     size_t per_row = (size_t)P.width * P.samples;
     size_t max_rays = 4u << 20;
+    if (const char *e = getenv("CGRT_EYE_CHUNK")) { long long c = atoll(e); if (c > 0) max_rays = (size_t)c; }  // tests: force many chunks / queue growth
     int rows_per_chunk = (int)(max_rays / per_row);
     if (rows_per_chunk < 1) rows_per_chunk = 1;
     for (int r0 = y0; r0 < y1; r0 += rows_per_chunk) {
@@ -884,7 +885,7 @@ int cgrt_eye_pass(cgrt_ctx *ctx, int y0, int y1) {
         size_t n = (size_t)(r1 - r0) * per_row;
         int cur = 0;
         for (int depth = 0; depth < P.max_depth && n > 0; depth++) {
-            CKS(ensure_queues(ctx, 2 * n > max_rays ? 2 * n : max_rays));
+            CKS(ensure_queue(ctx, cur ^ 1, 2 * n > max_rays ? 2 * n : max_rays));  // glass splits: at most two children per ray
             CKS(ensure_hp_capacity(ctx, (size_t)ctx->hp_count + n));
             CK(cudaMemsetAsync(ctx->d_qcount + (cur ^ 1), 0, sizeof(unsigned int), ctx->stream));
             if (depth == 0)

@@ -380,3 +380,37 @@ def test_chunked_and_pipelined_photon_pass(gpu, oracle_lib, overlap, monkeypatch
             g.round_update(); o.round_update()
         assert np.allclose(g.gather_image(90000.0), o.gather_image(90000.0), rtol=1e-9, atol=1e-12)
         assert g.counters()["gpu_launches"] > 3 * 5 * 12
+
+
+def test_dof_camera_and_samples_bit_exact(gpu, oracle_lib):
+    """BASELINE config 4: thin-lens camera (main.cpp:203-207) with num_of_samples > 1 over the displaced floor and the objtype-2 mesh.
+    Run twice in one process: the second context re-uses pooled device memory, so anything read before it is written shows up."""
+    s = gpu.preset("c4_bump_dof")
+    cfg = gpu.RenderConfig(width=160, height=96, use_dof=1, num_of_samples=4, consume_dof_rng=1)
+    o = oracle_lib.Oracle(s, cfg)
+    o.eye_pass()
+    b = o.download_hitpoints()
+    for attempt in range(2):
+        with gpu.Context(0, s, cfg) as g:
+            g.eye_pass(); g.build_grid()
+            a = g.download_hitpoints()
+            assert len(a["pos"]) == len(b["pos"]) > 160 * 96 * 4 * 0.9, (attempt, len(a["pos"]), len(b["pos"]))
+            for k in ("key", "hw", "pos", "normal", "f", "r2"):
+                assert np.array_equal(a[k], b[k]), (attempt, k)
+            assert g.counters()["eye_segments"] == o.counters()["eye_segments"]
+
+
+def test_eye_pass_small_chunks_and_queue_growth(gpu, oracle_lib, monkeypatch):
+    """Many eye-pass chunks with ray queues that have to grow while the wavefront is alive (glass doubles the rays per bounce)."""
+    monkeypatch.setenv("CGRT_EYE_CHUNK", "300")
+    s = gpu.preset("c2_bunny_chess")
+    cfg = gpu.RenderConfig(width=256, height=192)
+    o = oracle_lib.Oracle(s, cfg)
+    o.eye_pass()
+    b = o.download_hitpoints()
+    with gpu.Context(0, s, cfg) as g:
+        g.eye_pass(); g.build_grid()
+        a = g.download_hitpoints()
+    assert len(a["pos"]) == len(b["pos"]) > 256 * 192
+    for k in ("key", "hw", "pos", "normal", "f"):
+        assert np.array_equal(a[k], b[k]), k
