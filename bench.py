@@ -277,7 +277,8 @@ def run_gpu(args):
                                              "photon_trace_kernel<continuation> x5": 1e3 * t_cont}},
         "photon_deposit_kernel": {"seconds": t_dep, "alg_bytes": bytes_dep, "gbps": bytes_dep / t_dep / 1e9, "launches": n_chunks,
                                   "ms_per_launch": 1e3 * t_dep / n_chunks, "candidates_per_hit": cand / max(1, hits),
-                                  "deposits_per_hit": dep / max(1, hits), "hits_per_s": hits / t_dep, "diffuse_hits": hits, "gathered_hits": gathered},
+                                  "deposits_per_hit": dep / max(1, hits), "hits_per_s": hits / t_dep, "diffuse_hits": hits, "gathered_hits": gathered,
+                                  "exact_tests_per_hit": (cp1["exact_tests"] - cp0["exact_tests"]) / max(1, hits)},
         "bin_scan+bin_scatter_kernel": {"seconds": t_sort, "launches": 3 * n_chunks},
         "round_update_kernel": {"seconds": t_upd, "launches": 1},
     }
@@ -320,7 +321,7 @@ def run_gpu(args):
                        f"grid + {args.e2e_rounds} rounds x {P} photons + updates + fp64 image and 8-bit image download, wall clock"}
 
     # ---- CPU baseline beside it (bounded sample)
-    cpu = cpu_baseline(scene, make_config(RenderConfig, update_mode=1, into_rule=0), args.cpu_photons) if args.cpu_photons > 0 else None
+    cpu = cpu_baseline(scene, make_config(RenderConfig, update_mode=1, into_rule=0), args.cpu_photons) if (args.cpu_photons > 0 and world == 1) else None
 
     line = {
         "metric": "photons_per_s", "value": value, "unit": "photons/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,

@@ -41,7 +41,7 @@ class CgrtConfig(C.Structure):
 
 class CgrtCounters(C.Structure):
     _fields_ = [(n, C.c_uint64) for n in (
-        "eye_segments", "photon_segments", "diffuse_hits", "candidates", "deposits", "node_visits", "tri_tests", "hitpoints", "gpu_launches", "gathered_hits")]
+        "eye_segments", "photon_segments", "diffuse_hits", "candidates", "deposits", "node_visits", "tri_tests", "hitpoints", "gpu_launches", "gathered_hits", "exact_tests")]
 
 
 class CgrtError(RuntimeError):

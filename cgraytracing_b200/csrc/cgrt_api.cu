@@ -1279,6 +1279,7 @@ int cgrt_get_counters(cgrt_ctx *ctx, cgrt_counters *out) {
     out->candidates = c.candidates;
     out->deposits = c.deposits;
     out->gathered_hits = c.gathered_hits;
+    out->exact_tests = c.exact_tests;
     {
         TravCounters tc;
         CK(cudaMemcpy(&tc, ctx->d_tc, sizeof tc, cudaMemcpyDeviceToHost));

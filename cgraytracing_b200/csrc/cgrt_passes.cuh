@@ -64,7 +64,7 @@ __device__ __forceinline__ void push_ray(const RayQueue &q, unsigned int s, d3 o
 }
 
 struct Counters {
-    unsigned long long eye_segments, photon_segments, diffuse_hits, candidates, deposits, gathered_hits;
+    unsigned long long eye_segments, photon_segments, diffuse_hits, candidates, deposits, gathered_hits, exact_tests;
 };
 
 // =================================================================================================================
@@ -608,7 +608,7 @@ __global__ void __launch_bounds__(CGRT_DEPOSIT_BLOCK) photon_deposit_kernel(cons
     const size_t warp = ((size_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     const size_t nwarps = ((size_t)gridDim.x * blockDim.x) >> 5;
     unsigned long long cand_total = 0;
-    unsigned int ndep = 0;
+    unsigned int ndep = 0, npair = 0;
     const int idx = lane / 9, idy = (lane / 3) % 3, idz = lane % 3;  // idx outermost, idz innermost (main.cpp:110-112)
     int qn = 0;
     const size_t n_slots = (size_t)__ldg(n_valid);
@@ -727,6 +727,7 @@ __global__ void __launch_bounds__(CGRT_DEPOSIT_BLOCK) photon_deposit_kernel(cons
                         const unsigned int pm = __ballot_sync(0xffffffffu, has);
                         if (has) queue[qn + __popc(pm & lt)] = make_uint2((uint32_t)lane, cidx[b]);
                         qn += __popc(pm);
+                        npair += (lane == 0) ? (unsigned int)__popc(pm) : 0u;
                         if (qn >= 32) {
                             __syncwarp();
                             const uint2 pr = queue[qn - 32 + lane];
@@ -757,6 +758,7 @@ __global__ void __launch_bounds__(CGRT_DEPOSIT_BLOCK) photon_deposit_kernel(cons
     if (lane == 0) {
         if (cand_total) atomicAdd(&ctr->candidates, cand_total);
         if (dep_total) atomicAdd(&ctr->deposits, dep_total);
+        if (npair) atomicAdd(&ctr->exact_tests, (unsigned long long)npair);
     }
 }
 

@@ -56,6 +56,7 @@ typedef struct cgrt_counters {
     uint64_t hitpoints;                     /* "hitpoints: %d", main.cpp:265 */
     uint64_t gpu_launches;                  /* kernels launched by this ctx so far */
     uint64_t gathered_hits;                 /* diffuse hits that went through the 27-cell gather (= diffuse_hits unless culling is on) */
+    uint64_t exact_tests;                   /* (hit, hitpoint) pairs that passed the fp32 prefilter and took the fp64 test of main.cpp:116 */
 } cgrt_counters;
 
 /* ---- lifecycle ------------------------------------------------------------------------------------------------ */
