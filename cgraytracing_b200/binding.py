@@ -26,7 +26,7 @@ ABI_SYMBOLS = [
     "cgrt_intersect_batch", "cgrt_hash_keys", "cgrt_surface_color", "cgrt_object_triangles", "cgrt_sample", "cgrt_radix_sort",
     "cgrt_count_traversal", "cgrt_eye_pass", "cgrt_export_hitpoints_dev", "cgrt_import_hitpoints_dev", "cgrt_build_grid", "cgrt_photon_pass",
     "cgrt_accum_dev", "cgrt_allreduce_accum", "cgrt_round_update", "cgrt_gather_image", "cgrt_num_hitpoints", "cgrt_download_hitpoints",
-    "cgrt_download_accum", "cgrt_download_grid", "cgrt_get_counters", "cgrt_get_timings", "cgrt_set_counting", "cgrt_set_profiling", "cgrt_set_culling", "cgrt_set_overlap",
+    "cgrt_download_accum", "cgrt_download_grid", "cgrt_get_counters", "cgrt_get_timings", "cgrt_set_counting", "cgrt_set_profiling", "cgrt_set_culling", "cgrt_set_overlap", "cgrt_average_u8", "cgrt_average_f64",
 ]
 
 
@@ -248,6 +248,26 @@ class Context:
         rgb8 = np.zeros((self.cfg.height, self.cfg.width, 3), np.uint8) if want_rgb8 else None
         self._ck(self.L.cgrt_gather_image(self.h, C.c_double(n_emitted), _p(img, c_dp), _p(rgb8, c_u8p)))
         return (img, rgb8) if want_rgb8 else img
+
+    # -- multi-run averaging (average.cpp)
+    def average_u8(self, images):
+        imgs = [np.ascontiguousarray(im, dtype=np.uint8) for im in images]
+        n, nbytes = len(imgs), imgs[0].size
+        assert all(im.size == nbytes for im in imgs)
+        ptrs = (c_u8p * n)(*[_p(im, c_u8p) for im in imgs])
+        out = np.zeros(imgs[0].shape, np.uint8)
+        self._ck(self.L.cgrt_average_u8(self.h, n, ptrs, C.c_int64(nbytes), _p(out, c_u8p)))
+        return out
+
+    def average_f64(self, images, want_rgb8=False):
+        imgs = [_d(im) for im in images]
+        n, nv = len(imgs), imgs[0].size
+        assert all(im.size == nv for im in imgs)
+        ptrs = (c_dp * n)(*[_p(im, c_dp) for im in imgs])
+        mean = np.zeros(imgs[0].shape)
+        rgb8 = np.zeros(imgs[0].shape, np.uint8) if want_rgb8 else None
+        self._ck(self.L.cgrt_average_f64(self.h, n, ptrs, C.c_int64(nv), _p(mean, c_dp), _p(rgb8, c_u8p)))
+        return (mean, rgb8) if want_rgb8 else mean
 
     # -- downloads
     def num_hitpoints(self):

@@ -1197,6 +1197,46 @@ int cgrt_gather_image(cgrt_ctx *ctx, double n_emitted, double *rgb, uint8_t *rgb
     return CGRT_OK;
 }
 
+// ---- multi-run averaging (average.cpp) ------------------------------------------------------------------------------
+int cgrt_average_u8(cgrt_ctx *ctx, int n, const uint8_t *const *imgs, int64_t nbytes, uint8_t *out) {
+    if (!ctx || n <= 0 || n > 255 || !imgs || nbytes < 0 || !out) return CGRT_ERR_INVALID;
+    if (nbytes == 0) return CGRT_OK;
+    CK(cudaSetDevice(ctx->device));
+    uint8_t *d_in, *d_out;
+    CKS(dalloc(ctx, &d_in, (size_t)n * (size_t)nbytes));
+    CKS(dalloc(ctx, &d_out, (size_t)nbytes));
+    for (int k = 0; k < n; k++) {
+        if (!imgs[k]) FAIL(CGRT_ERR_INVALID, "null image");
+        CK(cudaMemcpyAsync(d_in + (size_t)k * (size_t)nbytes, imgs[k], (size_t)nbytes, cudaMemcpyHostToDevice, ctx->stream));
+    }
+    average_u8_kernel<<<nblk((size_t)nbytes, 256), 256, 0, ctx->stream>>>(d_in, n, nbytes, d_out);
+    ctx->launches++;
+    CK(cudaGetLastError());
+    CKS(download_free(ctx, out, d_out, (size_t)nbytes));
+    return dfree(ctx, d_in);
+}
+
+int cgrt_average_f64(cgrt_ctx *ctx, int n, const double *const *imgs, int64_t nvalues, double *mean, uint8_t *rgb8) {
+    if (!ctx || n <= 0 || !imgs || nvalues < 0 || !mean) return CGRT_ERR_INVALID;
+    if (nvalues == 0) return CGRT_OK;
+    CK(cudaSetDevice(ctx->device));
+    double *d_in, *d_mean;
+    uint8_t *d_rgb8 = nullptr;
+    CKS(dalloc(ctx, &d_in, (size_t)n * (size_t)nvalues));
+    CKS(dalloc(ctx, &d_mean, (size_t)nvalues));
+    if (rgb8) CKS(dalloc(ctx, &d_rgb8, (size_t)nvalues));
+    for (int k = 0; k < n; k++) {
+        if (!imgs[k]) FAIL(CGRT_ERR_INVALID, "null image");
+        CK(cudaMemcpyAsync(d_in + (size_t)k * (size_t)nvalues, imgs[k], (size_t)nvalues * sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
+    }
+    average_f64_kernel<<<nblk((size_t)nvalues, 256), 256, 0, ctx->stream>>>(d_in, n, nvalues, d_mean, d_rgb8);
+    ctx->launches++;
+    CK(cudaGetLastError());
+    CKS(download_free(ctx, mean, d_mean, (size_t)nvalues));
+    if (rgb8) CKS(download_free(ctx, rgb8, d_rgb8, (size_t)nvalues));
+    return dfree(ctx, d_in);
+}
+
 // ---- downloads -----------------------------------------------------------------------------------------------------
 int cgrt_num_hitpoints(cgrt_ctx *ctx, int64_t *n) {
     if (!ctx || !n) return CGRT_ERR_INVALID;

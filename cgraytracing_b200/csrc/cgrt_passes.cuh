@@ -888,6 +888,27 @@ __global__ void image_gather_kernel(int width, int height, double n_emitted, con
 }
 
 // =================================================================================================================
+// average.cpp:19-65: out = sum_k (img_k / n) per byte (integer division first, then the sum), and its linear-domain counterpart.
+// The n images are stored back to back in `imgs` (n x count).
+// =================================================================================================================
+__global__ void average_u8_kernel(const uint8_t *__restrict__ imgs, int n, int64_t count, uint8_t *__restrict__ out) {
+    int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= count) return;
+    unsigned int acc = 0;
+    for (int k = 0; k < n; k++) acc += (unsigned int)imgs[(size_t)k * count + i] / (unsigned int)n;
+    out[i] = (uint8_t)acc;  // imgdata[] is unsigned char: wraps like the reference would (it cannot for n >= 1: n * floor(255 / n) <= 255)
+}
+__global__ void average_f64_kernel(const double *__restrict__ imgs, int n, int64_t count, double *__restrict__ mean, uint8_t *__restrict__ rgb8) {
+    int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= count) return;
+    double acc = 0.0;
+    for (int k = 0; k < n; k++) acc += imgs[(size_t)k * count + i];
+    acc = acc / (double)n;
+    mean[i] = acc;
+    if (rgb8) rgb8[i] = (uint8_t)(char)gamma_corr(acc);
+}
+
+// =================================================================================================================
 // Parity-hook kernels
 // =================================================================================================================
 template <bool COUNT>

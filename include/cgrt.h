@@ -133,6 +133,14 @@ int cgrt_round_update(cgrt_ctx *ctx);
 /* main.cpp:252-258 (+ :403-411 when rgb8 != NULL: tone map, gamma, vertical flip). rgb: H*W*3 fp64, row h = image[h]. */
 int cgrt_gather_image(cgrt_ctx *ctx, double n_emitted, double *rgb, uint8_t *rgb8);
 
+/* ---- multi-run averaging (average.cpp:19-65), the reference's way of combining separately rendered images ------------ */
+/* Bit-exact 8-bit mode: out[i] = sum over the n images of (img_k[i] / n) in integer arithmetic, exactly what average.cpp does with
+ * n = 9 (truncating division before the sum; never overflows a byte). imgs: n host pointers to nbytes bytes each. */
+int cgrt_average_u8(cgrt_ctx *ctx, int n, const uint8_t *const *imgs, int64_t nbytes, uint8_t *out);
+/* Linear mode: mean of n fp64 radiance images (what cgrt_gather_image returns), optionally tone-mapped like main.cpp:403-411
+ * into rgb8 (no vertical flip: the inputs are image[h][w] arrays, the output keeps their row order). rgb8 may be NULL. */
+int cgrt_average_f64(cgrt_ctx *ctx, int n, const double *const *imgs, int64_t nvalues, double *mean, uint8_t *rgb8);
+
 /* ---- downloads (canonical order: bucket ascending, creation order inside a bucket; main.cpp:252-254) ------------- */
 int cgrt_num_hitpoints(cgrt_ctx *ctx, int64_t *n);
 int cgrt_download_hitpoints(cgrt_ctx *ctx, double *pos, double *normal, double *f, double *flux, double *r2, int32_t *n,

@@ -295,6 +295,16 @@ def tonemap_flip(img):
     return out
 
 
+def average_u8(images):
+    """average.cpp: per byte, sum of img/n over the n images."""
+    imgs = [np.ascontiguousarray(im, dtype=np.uint8) for im in images]
+    n = len(imgs)
+    ptrs = (c_u8p * n)(*[_p(im, c_u8p) for im in imgs])
+    out = np.zeros(imgs[0].shape, np.uint8)
+    orc_lib().orc_average_u8(n, ptrs, C.c_int64(imgs[0].size), _p(out, c_u8p))
+    return out
+
+
 def det_inv(a, b, c):
     d = C.c_double(0); inv9 = np.zeros(9)
     ok = orc_lib().orc_det_inv(_p(_d(a), c_dp), _p(_d(b), c_dp), _p(_d(c), c_dp), C.byref(d), _p(inv9, c_dp))

@@ -452,6 +452,19 @@ int orc_tonemap_flip(int width, int height, const double *rgb, uint8_t *out) {
     return 0;
 }
 
+// average.cpp:19-65: imgdata[i] = sum over the n images of img_k[i] / n (unsigned char arithmetic, division before the sum).
+int orc_average_u8(int n, const uint8_t *const *imgs, int64_t nbytes, uint8_t *out) {
+    for (int64_t i = 0; i < nbytes; i++) {
+        unsigned char acc = 0;
+        for (int k = 0; k < n; k++) {
+            if (k == 0) acc = (unsigned char)(imgs[k][i] / n);
+            else acc += (unsigned char)(imgs[k][i] / n);
+        }
+        out[i] = acc;
+    }
+    return 0;
+}
+
 int orc_get_counters(void *c_, orc_counters *o) {
     Ctx *c = (Ctx *)c_;
     const Counters &k = c->R.ctr;
