@@ -1062,17 +1062,19 @@ int cgrt_photon_pass(cgrt_ctx *ctx, uint64_t first, uint64_t count) {
                 PhotonState *qin = ctx->pq[(pass - 1) & 1];
                 PhotonState *qout = ctx->pq[pass & 1];
                 const unsigned int *nin = qc + pass - 1;
-                if (ctx->S.nbez > 0) {  // the Newton solver costs registers: meshes-only scenes run the lean variant
-                    if (ctx->counting) photon_traverse_kernel<true, true><<<resume_grid, 128, 0, T>>>(ctx->S, qin, nin, ctx->d_tc);
-                    else photon_traverse_kernel<false, true><<<resume_grid, 128, 0, T>>>(ctx->S, qin, nin, ctx->d_tc);
-                } else {
-                    if (ctx->counting) photon_traverse_kernel<true, false><<<resume_grid, 128, 0, T>>>(ctx->S, qin, nin, ctx->d_tc);
-                    else photon_traverse_kernel<false, false><<<resume_grid, 128, 0, T>>>(ctx->S, qin, nin, ctx->d_tc);
+                if (ctx->S.nbez > 0) {
+                    photon_bezier_kernel<<<resume_grid, 128, 0, T>>>(ctx->S, qin, nin);
+                    ctx->launches++;
+                }
+                if (ctx->S.nbvh > 0) {
+                    if (ctx->counting) photon_traverse_kernel<true><<<resume_grid, 128, 0, T>>>(ctx->S, qin, nin, ctx->d_tc);
+                    else photon_traverse_kernel<false><<<resume_grid, 128, 0, T>>>(ctx->S, qin, nin, ctx->d_tc);
+                    ctx->launches++;
                 }
                 stamp(7);
                 LAUNCH_PT(false, ctx->grid_cont, qin, nin, qout, qc + pass);
                 stamp(8);
-                ctx->launches += 2;
+                ctx->launches++;
             }
         }
 #undef LAUNCH_PT

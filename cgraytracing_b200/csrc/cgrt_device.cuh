@@ -421,63 +421,60 @@ __device__ __forceinline__ d3 bez_F(const BezDev &Z, d3 par, d3 o, d3 d, d3 &P, 
     return o + d * par.x - mk(Z.pos[0], Z.pos[1], Z.pos[2]) - surf;
 }
 
-__device__ bool bezier_intersect(const BezDev &Z, d3 o, d3 d, double &len, d3 &nrm) {
-    if (!box_any_face_hit(Z.box, o, d)) return false;
-    bool flag = false;
-    len = CGRT_INF;
-    d3 pos = mk(Z.pos[0], Z.pos[1], Z.pos[2]);
-    // Entry/exit of the ray through the bounding cylinder's slab gives the t range worth seeding.
-    // Seeds: 4 values of u x 3 values of t across [tlo, thi] (theta from the seed point, bezier.h:243-247).
-    double rmax = Z.box[0] - Z.pos[0];
-    double tc = dot(pos - o, d);           // closest approach to the axis point
-    double tlo = fmax(tc - 2.0 * rmax - (Z.box[2] - Z.box[3]), 0.0), thi = tc + 2.0 * rmax + (Z.box[2] - Z.box[3]);
-    for (int iu = 0; iu < 4; iu++) {
-        for (int it = 0; it < 4; it++) {
-            double u0 = (iu + 0.5) * 0.25;
-            double t0 = tlo + (thi - tlo) * (it + 0.5) * 0.25;
-            d3 pt = o + d * t0 - pos;
-            double theta = (pt.z < 0) ? 3.14159265 + atan(pt.x / pt.z) : atan(pt.x / pt.z);
-            d3 par = mk(t0, u0, theta);
-            d3 P, dP;
-            d3 F = bez_F(Z, par, o, d, P, dP);
-            int iter = 0;
-            while (sqrt(dot(F, F)) > 1e-6 && iter < 100) {  // bezier.h:170
-                iter++;
-                double s, c;
-                sincos(par.z, &s, &c);
-                // Jacobian columns (bezier.h:150-162)
-                d3 a = d;
-                d3 b = mk(-s * dP.z, -dP.y, -c * dP.z);
-                d3 cc = mk(-c * P.z, 0.0, s * P.z);
-                double D = det3(a, b, cc);
-                if (D < 1e-4 && D > -1e-4) {  // vec3.h:105: singular -> the reference jitters; we nudge deterministically
-                    par = mk(par.x + 0.037, par.y + 0.029 * ((iter & 1) ? 1 : -1), par.z + 0.041);
-                    F = bez_F(Z, par, o, d, P, dP);
-                    continue;
-                }
-                // inverse (vec3.h:109-117) applied to F (vec3.h:99-101)
-                d3 ra = mk((b.y * cc.z - b.z * cc.y) / D, (cc.y * a.z - cc.z * a.y) / D, (a.y * b.z - a.z * b.y) / D);
-                d3 rb = mk((cc.x * b.z - cc.z * b.x) / D, (a.x * cc.z - a.z * cc.x) / D, (b.x * a.z - b.z * a.x) / D);
-                d3 rc = mk((b.x * cc.y - cc.x * b.y) / D, (cc.x * a.y - cc.y * a.x) / D, (a.x * b.y - a.y * b.x) / D);
-                d3 step = ra * F.x + rb * F.y + rc * F.z;
-                par = par - step;
-                F = bez_F(Z, par, o, d, P, dP);
-            }
-            if (sqrt(dot(F, F)) < 1e-4 && par.x > 0 && par.y <= 1 && par.y >= 0) {  // bezier.h:257
-                if (par.x < len) {
-                    len = par.x;
-                    // bezier.h:215-224
-                    d3 g = normalize(dP);
-                    double s, c;
-                    sincos(par.z, &s, &c);
-                    nrm = mk(g.y * s, -g.z, g.y * c);
-                    flag = true;
-                }
-            }
+// One Newton solve (bezier.h:163-214) from seed number `seed` of the deterministic 4 x 4 grid (u0 = 1/8, 3/8, 5/8, 7/8 times four
+// t0 across the ray's passage by the axis; theta0 from the seed point, bezier.h:243-247). Returns whether the iterate is accepted
+// (bezier.h:257) and then its t and the un-oriented normal of bezier.h:215-224.
+#define CGRT_BEZ_SEEDS 16
+__device__ __forceinline__ bool bezier_newton_seed(const BezDev &Z, d3 o, d3 d, int seed, double &t_out, d3 &nrm_out) {
+    const d3 pos = mk(Z.pos[0], Z.pos[1], Z.pos[2]);
+    const double rmax = Z.box[0] - Z.pos[0];
+    const double tc = dot(pos - o, d);  // closest approach to the axis point
+    const double tlo = fmax(tc - 2.0 * rmax - (Z.box[2] - Z.box[3]), 0.0), thi = tc + 2.0 * rmax + (Z.box[2] - Z.box[3]);
+    const int iu = seed >> 2, it = seed & 3;
+    double u0 = (iu + 0.5) * 0.25;
+    double t0 = tlo + (thi - tlo) * (it + 0.5) * 0.25;
+    d3 pt = o + d * t0 - pos;
+    double theta = (pt.z < 0) ? 3.14159265 + atan(pt.x / pt.z) : atan(pt.x / pt.z);
+    d3 par = mk(t0, u0, theta);
+    d3 P, dP;
+    d3 F = bez_F(Z, par, o, d, P, dP);
+    int iter = 0;
+    while (sqrt(dot(F, F)) > 1e-6 && iter < 100) {  // bezier.h:170
+        iter++;
+        double s, c;
+        sincos(par.z, &s, &c);
+        // Jacobian columns (bezier.h:150-162)
+        d3 a = d;
+        d3 b = mk(-s * dP.z, -dP.y, -c * dP.z);
+        d3 cc = mk(-c * P.z, 0.0, s * P.z);
+        double D = det3(a, b, cc);
+        if (D < 1e-4 && D > -1e-4) {  // vec3.h:105: singular -> the reference jitters; we nudge deterministically
+            par = mk(par.x + 0.037, par.y + 0.029 * ((iter & 1) ? 1 : -1), par.z + 0.041);
+            F = bez_F(Z, par, o, d, P, dP);
+            continue;
         }
+        // inverse (vec3.h:109-117) applied to F (vec3.h:99-101)
+        d3 ra = mk((b.y * cc.z - b.z * cc.y) / D, (cc.y * a.z - cc.z * a.y) / D, (a.y * b.z - a.z * b.y) / D);
+        d3 rb = mk((cc.x * b.z - cc.z * b.x) / D, (a.x * cc.z - a.z * cc.x) / D, (b.x * a.z - b.z * a.x) / D);
+        d3 rc = mk((b.x * cc.y - cc.x * b.y) / D, (cc.x * a.y - cc.y * a.x) / D, (a.x * b.y - a.y * b.x) / D);
+        d3 step = ra * F.x + rb * F.y + rc * F.z;
+        par = par - step;
+        F = bez_F(Z, par, o, d, P, dP);
     }
-    nrm = nrm * ((dot(nrm, d) < 0) ? 1.0 : -1.0);  // bezier.h:272
-    double newt = Z.box[2] - o.y;                  // bezier.h:273-281 top cap
+    if (!(sqrt(dot(F, F)) < 1e-4 && par.x > 0 && par.y <= 1 && par.y >= 0)) return false;  // bezier.h:257
+    t_out = par.x;
+    d3 g = normalize(dP);  // bezier.h:215-224
+    double s, c;
+    sincos(par.z, &s, &c);
+    nrm_out = mk(g.y * s, -g.z, g.y * c);
+    return true;
+}
+// bezier.h:272-281: orient the normal against the ray, then the top-cap disc (which overrides len even when farther, but is only
+// reported when Newton also hit, bezier.h:289).
+__device__ __forceinline__ void bezier_finish(const BezDev &Z, d3 o, d3 d, double &len, d3 &nrm) {
+    const d3 pos = mk(Z.pos[0], Z.pos[1], Z.pos[2]);
+    nrm = nrm * ((dot(nrm, d) < 0) ? 1.0 : -1.0);
+    double newt = Z.box[2] - o.y;
     if (newt > 0.1) {
         newt = newt / d.y;
         d3 np = o + d * newt;
@@ -486,7 +483,40 @@ __device__ bool bezier_intersect(const BezDev &Z, d3 o, d3 d, double &len, d3 &n
             nrm = mk(0, 1, 0);
         }
     }
+}
+// Bezier::intersect (bezier.h:225-290), one thread: the seeds in order, the nearest accepted root wins (the first one on ties).
+__device__ bool bezier_intersect(const BezDev &Z, d3 o, d3 d, double &len, d3 &nrm) {
+    if (!box_any_face_hit(Z.box, o, d)) return false;
+    bool flag = false;
+    len = CGRT_INF;
+    for (int seed = 0; seed < CGRT_BEZ_SEEDS; seed++) {
+        double t; d3 nv;
+        if (bezier_newton_seed(Z, o, d, seed, t, nv) && t < len) { len = t; nrm = nv; flag = true; }
+    }
+    bezier_finish(Z, o, d, len, nrm);
     return flag;
+}
+// The same for one ray per HALF-WARP: lane j of the half runs seed j, the minimum of (t, seed) is found by shuffles. All 16 lanes of
+// the half must call it with the same ray; every lane returns the result.
+__device__ __forceinline__ bool bezier_intersect_halfwarp(const BezDev &Z, d3 o, d3 d, double &len, d3 &nrm) {
+    const unsigned int lane = threadIdx.x & 31u, half_mask = (lane < 16u) ? 0x0000ffffu : 0xffff0000u;
+    if (!box_any_face_hit(Z.box, o, d)) return false;  // uniform within the half
+    double t = CGRT_INF; d3 nv = mk(0, 0, 0);
+    bool ok = bezier_newton_seed(Z, o, d, (int)(lane & 15u), t, nv);
+    if (!ok) t = CGRT_INF;
+    int who = ok ? (int)(lane & 15u) : 16;
+#pragma unroll
+    for (int off = 8; off >= 1; off >>= 1) {  // lexicographic minimum of (t, seed) over the 16 lanes
+        double t2 = __shfl_xor_sync(half_mask, t, off);
+        int w2 = __shfl_xor_sync(half_mask, who, off);
+        if (t2 < t || (t2 == t && w2 < who)) { t = t2; who = w2; }
+    }
+    if (who >= 16) return false;
+    const int src = (int)(lane & 16u) + who;
+    nv.x = __shfl_sync(half_mask, nv.x, src); nv.y = __shfl_sync(half_mask, nv.y, src); nv.z = __shfl_sync(half_mask, nv.z, src);
+    len = t; nrm = nv;
+    bezier_finish(Z, o, d, len, nrm);
+    return true;
 }
 
 // ---------------------------------------------------------------------------------------------------------------
@@ -632,11 +662,27 @@ __device__ __forceinline__ bool closest_hit_block(const SceneDev &S, bool active
             sm.near_in[tid] = A.nearest; sm.id_in[tid] = A.id;
         }
         __syncthreads();
-        if (tid < (int)sm.count) {
+        if (O.kind == OBJ_BEZIER) {
+            // one listed ray per half-warp, one Newton seed per lane; every half runs the same number of rounds
+            const int half = tid >> 4, nhalf = BLOCK / 16, cnt = (int)sm.count;
+            for (int r = 0; r * nhalf < cnt; r++) {
+                const int e = r * nhalf + half;
+                const bool live = e < cnt;
+                const int s = live ? sm.list[e] : 0;
+                double len; d3 nv;
+                bool hit = live && bezier_intersect_halfwarp(S.bez[O.aux], mk(sm.ox[s], sm.oy[s], sm.oz[s]), mk(sm.dx[s], sm.dy[s], sm.dz[s]), len, nv);
+                if (live) __syncwarp((tid & 16) ? 0xffff0000u : 0x0000ffffu);  // all 16 lanes have read the ray before lane 0 overwrites it
+                hit = hit && (len < sm.near_in[s] || (len == sm.near_in[s] && i < sm.id_in[s]));
+                if (live && (tid & 15) == 0) {
+                    sm.leaf[s] = hit ? 1 : 0;
+                    if (hit) { sm.lim[s] = len; sm.ox[s] = nv.x; sm.oy[s] = nv.y; sm.oz[s] = nv.z; sm.id_in[s] = -1; }
+                }
+            }
+        } else if (tid < (int)sm.count) {
             int s = sm.list[tid];
             HitAcc R;
             R.nearest = sm.near_in[s]; R.id = sm.id_in[s]; R.prim = -1; R.nrm = mk(0, 0, 0);
-            bool hit = deferred_resolve<COUNT, true>(S, i, mk(sm.ox[s], sm.oy[s], sm.oz[s]), mk(sm.dx[s], sm.dy[s], sm.dz[s]), sm.lim[s], R, tc);
+            bool hit = deferred_resolve<COUNT, false>(S, i, mk(sm.ox[s], sm.oy[s], sm.oz[s]), mk(sm.dx[s], sm.dy[s], sm.dz[s]), sm.lim[s], R, tc);
             sm.leaf[s] = hit ? 1 : 0;
             if (hit) {
                 sm.lim[s] = R.nearest; sm.ox[s] = R.nrm.x; sm.oy[s] = R.nrm.y; sm.oz[s] = R.nrm.z; sm.id_in[s] = R.prim;

@@ -320,8 +320,8 @@ __device__ __forceinline__ uint32_t cell_bin(int ix, int iy, int iz) {
 
 // The BVH part of the closest hit for suspended photons: one thread per queue entry, every lane traverses (dense warps,
 // small register footprint). The winner of (analytic hit, mesh hits) is written back into the entry.
-template <bool COUNT, bool BEZ>
-__global__ void __launch_bounds__(128, BEZ ? 1 : CGRT_TRAV_MINB) photon_traverse_kernel(const __grid_constant__ SceneDev S, PhotonState *__restrict__ q,
+template <bool COUNT>
+__global__ void __launch_bounds__(128, CGRT_TRAV_MINB) photon_traverse_kernel(const __grid_constant__ SceneDev S, PhotonState *__restrict__ q,
                                                               const unsigned int *__restrict__ n_in, TravCounters *tcg) {
     const unsigned int total = *n_in;
     TravCounters tcl;
@@ -334,10 +334,10 @@ __global__ void __launch_bounds__(128, BEZ ? 1 : CGRT_TRAV_MINB) photon_traverse
         A.nearest = q[i].nearest; A.id = q[i].id; A.prim = -1; A.nrm = mk(0, 0, 0);
         bool changed = false;
         for (int k = 0; k < S.nobj; k++) {
-            if (!is_deferred(S.obj[k])) continue;
+            if (S.obj[k].bvh < 0) continue;  // Bezier objects were resolved by photon_bezier_kernel
             double lim;
             if (!deferred_wanted(S, k, o, d, A, lim)) continue;
-            changed |= deferred_resolve<COUNT, BEZ>(S, k, o, d, lim, A, &tcl);
+            changed |= deferred_resolve<COUNT, false>(S, k, o, d, lim, A, &tcl);
         }
         if (changed) {
             q[i].nearest = A.nearest;
@@ -352,6 +352,41 @@ __global__ void __launch_bounds__(128, BEZ ? 1 : CGRT_TRAV_MINB) photon_traverse
         if ((threadIdx.x & 31) == 0) {
             if (nn) atomicAdd(&tcg->node_visits, (unsigned long long)nn);
             if (nt_) atomicAdd(&tcg->tri_tests, (unsigned long long)nt_);
+        }
+    }
+}
+
+// Bezier surfaces of suspended photons: one queue entry per half-warp, one Newton seed per lane (the 16 solves of a ray run side by
+// side instead of one after the other in a single thread). Merges with the (len, object index) rule like everything else; the
+// traversal kernel that follows skips Bezier objects.
+__global__ void __launch_bounds__(128) photon_bezier_kernel(const __grid_constant__ SceneDev S, PhotonState *__restrict__ q, const unsigned int *__restrict__ n_in) {
+    const unsigned int total = *n_in;
+    const unsigned int half = (blockIdx.x * blockDim.x + threadIdx.x) >> 4, nhalf = (gridDim.x * blockDim.x) >> 4;
+    const unsigned int rounds = (total + nhalf - 1) / nhalf;
+    for (unsigned int r = 0; r < rounds; r++) {  // both halves of a warp run the same number of rounds: shuffles stay convergent
+        const unsigned int i = r * nhalf + half;
+        const bool live = i < total;
+        d3 o = mk(0, 0, 0), d = mk(0, 0, 1);
+        double nearest = CGRT_INF;
+        int id = -1;
+        if (live) {
+            const double2 *p = reinterpret_cast<const double2 *>(q + i);
+            double2 q0 = p[0], q1 = p[1], q2 = p[2];
+            o = mk(q0.x, q0.y, q1.x); d = mk(q1.y, q2.x, q2.y);
+            nearest = q[i].nearest; id = q[i].id;
+        }
+        for (int k = 0; k < S.nobj; k++) {
+            if (S.obj[k].kind != OBJ_BEZIER) continue;
+            double len; d3 nv;
+            bool hit = live && bezier_intersect_halfwarp(S.bez[S.obj[k].aux], o, d, len, nv);
+            if (hit && (len < nearest || (len == nearest && k < id))) {
+                nearest = len; id = k;
+                if ((threadIdx.x & 15) == 0) {
+                    q[i].nearest = len;
+                    q[i].nrm[0] = nv.x; q[i].nrm[1] = nv.y; q[i].nrm[2] = nv.z;
+                    q[i].id = k; q[i].prim = -1;
+                }
+            }
         }
     }
 }
