@@ -181,7 +181,10 @@ def run_gpu(args):
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
     scene = preset(PRESET)
     cfg = make_config(RenderConfig)
-    P = args.photons if args.photons > 0 else PHOTONS_PER_ROUND
+    # c5 is defined as 1 Gi photons per round IN TOTAL (the scaling sweep of the north star): strong scaling, every other workload
+    # keeps the photons per GPU fixed (weak scaling)
+    strong = WORKLOAD == "c5_dragon_4096" and args.photons <= 0
+    P = args.photons if args.photons > 0 else (PHOTONS_PER_ROUND // world if strong else PHOTONS_PER_ROUND)
     peak, peak_src = load_peaks()
 
     # ---- setup (untimed for `value`): scene upload + LBVH build, tile-sharded eye pass + all-gather, grid
@@ -325,7 +328,8 @@ def run_gpu(args):
 
     line = {
         "metric": "photons_per_s", "value": value, "unit": "photons/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
-        "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "strong" if strong else "weak", "vs_baseline": None, "dtype": "f64",
+        "data": "synthetic",
         "config": {"workload": WORKLOAD, "width": WIDTH, "height": HEIGHT, "photons_per_gpu_per_step": P, "hitpoints": c2["hitpoints"],
                    "triangles": scene.num_triangles(), "accum": "f64 atomics" if args.accum == 0 else "v4.f32 red",
                    "l2": "inputs larger than L2: every round writes and re-reads a fresh 8 GB deposit table (16 Mi photons x 5 bounces x 96 B) and new photons"},

@@ -100,6 +100,7 @@ struct cgrt_ctx {
     BvhBuild bvh_src[CGRT_MAX_BVH];
     int obj_bvh[CGRT_MAX_OBJECTS];
     std::vector<void *> allocs;
+    std::vector<std::pair<void *, size_t>> big_allocs;  // arena blocks (see dalloc)
 
     // hitpoints
     double *hp_rec = nullptr;  // raw records (12 doubles each), creation order of the wavefront
@@ -174,16 +175,36 @@ namespace {
         return (code);    \
     } while (0)
 
+// Small and medium buffers come from the stream-ordered pool (no device-wide sync, memory is reused); buffers of CGRT_ARENA_MIN bytes
+// or more (ray queues, hitpoint records) come from the process-wide arena of plain cudaMalloc blocks: growing the pool by gigabytes
+// was measured at 150-400 ms per context, a cudaMalloc of the same size at a few ms, and a parked block costs nothing.
+#define CGRT_ARENA_MIN ((size_t)32 << 20)
 template <typename T>
 int dalloc(cgrt_ctx *ctx, T **p, size_t n) {
     *p = nullptr;
     if (n == 0) n = 1;
-    CK(cudaMallocAsync((void **)p, n * sizeof(T), ctx->stream));  // stream-ordered pool: no device-wide sync, memory is reused
+    const size_t bytes = n * sizeof(T);
+    if (bytes >= CGRT_ARENA_MIN) {
+        void *q = arena_take(ctx->device, bytes);
+        if (!q) FAIL(CGRT_ERR_CUDA, "out of device memory");
+        ctx->big_allocs.push_back(std::make_pair(q, bytes));
+        *p = (T *)q;
+        return 0;
+    }
+    CK(cudaMallocAsync((void **)p, bytes, ctx->stream));
     ctx->allocs.push_back((void *)*p);
     return 0;
 }
 int dfree(cgrt_ctx *ctx, void *p) {
     if (!p) return 0;
+    for (size_t i = 0; i < ctx->big_allocs.size(); i++)
+        if (ctx->big_allocs[i].first == p) {
+            CK(cudaStreamSynchronize(ctx->stream));  // the next owner may be another context on another stream
+            arena_give(ctx->device, ctx->big_allocs[i].second, p);
+            ctx->big_allocs[i] = ctx->big_allocs.back();
+            ctx->big_allocs.pop_back();
+            return 0;
+        }
     for (size_t i = 0; i < ctx->allocs.size(); i++)
         if (ctx->allocs[i] == p) {
             ctx->allocs[i] = ctx->allocs.back();
@@ -551,6 +572,7 @@ int cgrt_destroy(cgrt_ctx *ctx) {
         }
     }
     for (int k = 0; k < 2; k++) arena_give(ctx->device, ctx->pq_cap * sizeof(PhotonState), ctx->pq[k]);
+    for (auto &b : ctx->big_allocs) arena_give(ctx->device, b.second, b.first);
     for (void *p : ctx->allocs) cudaFreeAsync(p, ctx->stream);
     cudaStreamSynchronize(ctx->stream);
     if (ctx->ev[0]) cudaEventDestroy(ctx->ev[0]);
