@@ -171,7 +171,7 @@ def run_gpu(args):
     import torch.distributed as dist
 
     from cgraytracing_b200 import Context, RenderConfig, preset
-    from cgraytracing_b200.distributed import GpuEngine, ShardedRenderer
+    from cgraytracing_b200.distributed import GpuEngine, ShardedRenderer, row_shard
 
     world = int(os.environ.get("WORLD_SIZE", "1"))
     rank = int(os.environ.get("RANK", "0"))
@@ -188,6 +188,14 @@ def run_gpu(args):
     peak, peak_src = load_peaks()
 
     # ---- setup (untimed for `value`): scene upload + LBVH build, tile-sharded eye pass + all-gather, grid
+    # a throw-away context first: it pays the process's one-time costs (module load, cudaMalloc of the arena blocks, which the
+    # library keeps for the process), so that the timed setup below is what every later render() in this process pays
+    with Context(local) as gw:
+        gw.set_config(cfg, accum_mode=args.accum)
+        scene.build_into(gw); gw.commit()
+        y0w, y1w = row_shard(HEIGHT, rank, world)
+        gw.eye_pass(y0w, y1w); gw.build_grid()
+        tmw = gw.timings()
     g = Context(local)
     g.set_config(cfg, accum_mode=args.accum)
     g.set_overlap(bool(args.overlap))
@@ -204,12 +212,11 @@ def run_gpu(args):
 
     # ---- roofline accounting (outside the timed region): counting build of the same traversal on a sample
     per_seg_nodes = per_seg_tris = None
-    eye_warm = None
+    eye_warm = (c0["eye_segments"], tm0["eye"], tm0["grid"])  # this rank's tile of the image (the whole image at world 1)
     if rank == 0:
         with Context(local) as gc:
             gc.set_config(cfg, accum_mode=args.accum)
             scene.build_into(gc); gc.commit(); gc.eye_pass(); gc.build_grid()
-            eye_warm = (gc.counters()["eye_segments"], gc.timings()["eye"], gc.timings()["grid"])  # second context: memory pool is warm
             gc.set_counting(True)
             gc.photon_pass(0, min(P, 1 << 20))
             cc = gc.counters()
@@ -335,10 +342,11 @@ def run_gpu(args):
                    "l2": "inputs larger than L2: every round writes and re-reads a fresh 8 GB deposit table (16 Mi photons x 5 bounces x 96 B) and new photons"},
         "s_per_round": ms * 1e-3 / args.steps, "eye_rays_per_s": eye_warm[0] / (eye_warm[1] * 1e-3),
         "segments_per_s": (c2["photon_segments"] - c1["photon_segments"]) * world / (ms * 1e-3),
-        "setup": {"commit_s": t_commit, "eye_ms_first_context": tm0["eye"], "grid_ms_first_context": tm0["grid"], "eye_ms": eye_warm[1],
+        "setup": {"commit_s": t_commit, "eye_ms_first_context": tmw["eye"], "grid_ms_first_context": tmw["grid"], "eye_ms": eye_warm[1],
                   "grid_ms": eye_warm[2], "eye_segments": eye_warm[0],
-                  "note": "eye_rays_per_s = segments of the whole-image eye pass / its device time (all bounce launches and their host "
-                          "synchronisations) in a context whose memory pool is warm; the first context of a process also pays pool growth"},
+                  "note": "eye_rays_per_s = segments of this rank's eye pass (the whole image at 1 GPU) / its device time (all bounce launches "
+                          "and their host synchronisations) in the second context of the process; the first context also pays the cudaMalloc "
+                          "of the arena blocks the library then keeps"},
         "roofline": roofline, "kernels": kernels, "cpu_baseline": cpu, "clocks": clocks, "e2e": e2e,
         "gpu_launches": int(c2["gpu_launches"] - c1["gpu_launches"]),
     }

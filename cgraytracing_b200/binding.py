@@ -27,6 +27,7 @@ ABI_SYMBOLS = [
     "cgrt_count_traversal", "cgrt_eye_pass", "cgrt_export_hitpoints_dev", "cgrt_import_hitpoints_dev", "cgrt_build_grid", "cgrt_photon_pass",
     "cgrt_accum_dev", "cgrt_allreduce_accum", "cgrt_round_update", "cgrt_gather_image", "cgrt_num_hitpoints", "cgrt_download_hitpoints",
     "cgrt_download_accum", "cgrt_download_grid", "cgrt_get_counters", "cgrt_get_timings", "cgrt_set_counting", "cgrt_set_profiling", "cgrt_set_culling", "cgrt_set_overlap", "cgrt_average_u8", "cgrt_average_f64",
+    "cgrt_check_guards",
 ]
 
 
@@ -307,6 +308,12 @@ class Context:
 
     def set_overlap(self, on=True):
         self._ck(self.L.cgrt_set_overlap(self.h, int(on)))
+
+    def check_guards(self) -> int:
+        """Damaged fence bytes so far (only meaningful when the process was started with CGRT_GUARD=1)."""
+        n = C.c_uint64(0)
+        self._ck(self.L.cgrt_check_guards(self.h, C.byref(n)))
+        return int(n.value)
 
     def set_profiling(self, on=True):
         self._ck(self.L.cgrt_set_profiling(self.h, int(on)))

@@ -8,6 +8,7 @@
 #include <cstring>
 #include <mutex>
 #include <string>
+#include <unordered_map>
 #include <utility>
 #include <vector>
 
@@ -101,6 +102,10 @@ struct cgrt_ctx {
     int obj_bvh[CGRT_MAX_OBJECTS];
     std::vector<void *> allocs;
     std::vector<std::pair<void *, size_t>> big_allocs;  // arena blocks (see dalloc)
+    // CGRT_GUARD=1 (dev): every device buffer is allocated with CGRT_GUARD_BYTES of 0xA5 on both sides; the fences are verified when
+    // the buffer is released and by cgrt_check_guards. user pointer -> (base pointer, user bytes)
+    std::unordered_map<void *, std::pair<void *, size_t>> guarded;
+    uint64_t guard_violations = 0;
 
     // hitpoints
     double *hp_rec = nullptr;  // raw records (12 doubles each), creation order of the wavefront
@@ -179,24 +184,71 @@ namespace {
 // or more (ray queues, hitpoint records) come from the process-wide arena of plain cudaMalloc blocks: growing the pool by gigabytes
 // was measured at 150-400 ms per context, a cudaMalloc of the same size at a few ms, and a parked block costs nothing.
 #define CGRT_ARENA_MIN ((size_t)32 << 20)
+#define CGRT_GUARD_BYTES ((size_t)4096)
+bool guard_mode() {
+    static const bool on = [] { const char *e = getenv("CGRT_GUARD"); return e && atoi(e) != 0; }();
+    return on;
+}
+// fences of one guarded buffer -> number of damaged bytes (synchronises the context's streams)
+uint64_t guard_damage(cgrt_ctx *ctx, void *base, size_t bytes) {
+    std::vector<unsigned char> h(2 * CGRT_GUARD_BYTES);
+    if (ctx->tstream) cudaStreamSynchronize(ctx->tstream);
+    cudaStreamSynchronize(ctx->stream);
+    cudaMemcpy(h.data(), base, CGRT_GUARD_BYTES, cudaMemcpyDeviceToHost);
+    cudaMemcpy(h.data() + CGRT_GUARD_BYTES, (char *)base + CGRT_GUARD_BYTES + bytes, CGRT_GUARD_BYTES, cudaMemcpyDeviceToHost);
+    uint64_t bad = 0;
+    for (unsigned char c : h) bad += c != 0xA5;
+    return bad;
+}
+// user pointer of a freshly allocated base block of bytes + 2 fences
+void *guard_wrap(cgrt_ctx *ctx, void *base, size_t bytes) {
+    cudaMemsetAsync(base, 0xA5, CGRT_GUARD_BYTES, ctx->stream);
+    cudaMemsetAsync((char *)base + CGRT_GUARD_BYTES + bytes, 0xA5, CGRT_GUARD_BYTES, ctx->stream);
+    void *user = (char *)base + CGRT_GUARD_BYTES;
+    ctx->guarded[user] = std::make_pair(base, bytes);
+    return user;
+}
+// base pointer of a guarded user pointer about to be released (fences verified); the pointer itself when guard mode is off
+void *guard_unwrap(cgrt_ctx *ctx, void *user) {
+    auto it = ctx->guarded.find(user);
+    if (it == ctx->guarded.end()) return user;
+    void *base = it->second.first;
+    ctx->guard_violations += guard_damage(ctx, base, it->second.second);
+    ctx->guarded.erase(it);
+    return base;
+}
+// the photon pass's tables: always arena blocks
+void *big_take(cgrt_ctx *ctx, size_t bytes) {
+    if (!guard_mode()) return arena_take(ctx->device, bytes);
+    void *base = arena_take(ctx->device, bytes + 2 * CGRT_GUARD_BYTES);
+    return base ? guard_wrap(ctx, base, bytes) : nullptr;
+}
+void big_give(cgrt_ctx *ctx, size_t bytes, void *p) {
+    if (!p) return;
+    const bool g = ctx->guarded.count(p) != 0;
+    arena_give(ctx->device, bytes + (g ? 2 * CGRT_GUARD_BYTES : 0), guard_unwrap(ctx, p));
+}
 template <typename T>
 int dalloc(cgrt_ctx *ctx, T **p, size_t n) {
     *p = nullptr;
     if (n == 0) n = 1;
-    const size_t bytes = n * sizeof(T);
+    const size_t user_bytes = (n * sizeof(T) + 15) & ~(size_t)15;
+    const size_t bytes = user_bytes + (guard_mode() ? 2 * CGRT_GUARD_BYTES : 0);
+    void *q = nullptr;
     if (bytes >= CGRT_ARENA_MIN) {
-        void *q = arena_take(ctx->device, bytes);
+        q = arena_take(ctx->device, bytes);
         if (!q) FAIL(CGRT_ERR_CUDA, "out of device memory");
         ctx->big_allocs.push_back(std::make_pair(q, bytes));
-        *p = (T *)q;
-        return 0;
+    } else {
+        CK(cudaMallocAsync(&q, bytes, ctx->stream));
+        ctx->allocs.push_back(q);
     }
-    CK(cudaMallocAsync((void **)p, bytes, ctx->stream));
-    ctx->allocs.push_back((void *)*p);
+    *p = (T *)(guard_mode() ? guard_wrap(ctx, q, user_bytes) : q);
     return 0;
 }
 int dfree(cgrt_ctx *ctx, void *p) {
     if (!p) return 0;
+    p = guard_unwrap(ctx, p);
     for (size_t i = 0; i < ctx->big_allocs.size(); i++)
         if (ctx->big_allocs[i].first == p) {
             CK(cudaStreamSynchronize(ctx->stream));  // the next owner may be another context on another stream
@@ -401,13 +453,13 @@ int ensure_photon_buffers(cgrt_ctx *ctx, size_t photons, size_t slots) {
         CK(cudaStreamSynchronize(ctx->tstream));
         CK(cudaStreamSynchronize(ctx->stream));
         if (b.cap) {
-            arena_give(ctx->device, b.cap * sizeof(DepositRec), b.rec);
-            arena_give(ctx->device, b.cap * sizeof(uint32_t), b.keys);
-            arena_give(ctx->device, b.cap * sizeof(uint32_t), b.perm);
+            big_give(ctx, b.cap * sizeof(DepositRec), b.rec);
+            big_give(ctx, b.cap * sizeof(uint32_t), b.keys);
+            big_give(ctx, b.cap * sizeof(uint32_t), b.perm);
         }
-        b.rec = (DepositRec *)arena_take(ctx->device, slots * sizeof(DepositRec));
-        b.keys = (uint32_t *)arena_take(ctx->device, slots * sizeof(uint32_t));
-        b.perm = (uint32_t *)arena_take(ctx->device, slots * sizeof(uint32_t));
+        b.rec = (DepositRec *)big_take(ctx, slots * sizeof(DepositRec));
+        b.keys = (uint32_t *)big_take(ctx, slots * sizeof(uint32_t));
+        b.perm = (uint32_t *)big_take(ctx, slots * sizeof(uint32_t));
         if (!b.rec || !b.keys || !b.perm) FAIL(CGRT_ERR_CUDA, "out of device memory for the deposit tables");
         b.cap = slots;
         b.drained_valid = false;
@@ -416,8 +468,8 @@ int ensure_photon_buffers(cgrt_ctx *ctx, size_t photons, size_t slots) {
     if (photons > ctx->pq_cap) {
         CK(cudaStreamSynchronize(ctx->tstream));
         for (int k = 0; k < 2; k++) {
-            if (ctx->pq_cap) arena_give(ctx->device, ctx->pq_cap * sizeof(PhotonState), ctx->pq[k]);
-            ctx->pq[k] = (PhotonState *)arena_take(ctx->device, photons * sizeof(PhotonState));
+            if (ctx->pq_cap) big_give(ctx, ctx->pq_cap * sizeof(PhotonState), ctx->pq[k]);
+            ctx->pq[k] = (PhotonState *)big_take(ctx, photons * sizeof(PhotonState));
             if (!ctx->pq[k]) FAIL(CGRT_ERR_CUDA, "out of device memory for the photon queues");
         }
         ctx->pq_cap = photons;
@@ -566,12 +618,17 @@ int cgrt_destroy(cgrt_ctx *ctx) {
         if (b.traced) cudaEventDestroy(b.traced);
         if (b.drained) cudaEventDestroy(b.drained);
         if (b.cap) {
-            arena_give(ctx->device, b.cap * sizeof(DepositRec), b.rec);
-            arena_give(ctx->device, b.cap * sizeof(uint32_t), b.keys);
-            arena_give(ctx->device, b.cap * sizeof(uint32_t), b.perm);
+            big_give(ctx, b.cap * sizeof(DepositRec), b.rec);
+            big_give(ctx, b.cap * sizeof(uint32_t), b.keys);
+            big_give(ctx, b.cap * sizeof(uint32_t), b.perm);
         }
     }
-    for (int k = 0; k < 2; k++) arena_give(ctx->device, ctx->pq_cap * sizeof(PhotonState), ctx->pq[k]);
+    for (int k = 0; k < 2; k++) big_give(ctx, ctx->pq_cap * sizeof(PhotonState), ctx->pq[k]);
+    if (!ctx->guarded.empty()) {
+        uint64_t bad = ctx->guard_violations;
+        for (auto &g : ctx->guarded) bad += guard_damage(ctx, g.second.first, g.second.second);
+        if (bad) fprintf(stderr, "cgrt: CGRT_GUARD found %llu damaged fence bytes in this context\n", (unsigned long long)bad);
+    }
     for (auto &b : ctx->big_allocs) arena_give(ctx->device, b.second, b.first);
     for (void *p : ctx->allocs) cudaFreeAsync(p, ctx->stream);
     cudaStreamSynchronize(ctx->stream);
@@ -1367,6 +1424,14 @@ int cgrt_set_overlap(cgrt_ctx *ctx, int on) {
     CK(cudaStreamSynchronize(ctx->tstream));
     CK(cudaStreamSynchronize(ctx->stream));
     ctx->overlap = on != 0;
+    return CGRT_OK;
+}
+
+int cgrt_check_guards(cgrt_ctx *ctx, uint64_t *damaged) {
+    if (!ctx || !damaged) return CGRT_ERR_INVALID;
+    uint64_t bad = ctx->guard_violations;
+    for (auto &g : ctx->guarded) bad += guard_damage(ctx, g.second.first, g.second.second);
+    *damaged = bad;
     return CGRT_OK;
 }
 

@@ -168,6 +168,10 @@ int cgrt_set_profiling(cgrt_ctx *ctx, int on);
  * [9] photon_trace_kernel<emission>, [7] photon_traverse_kernel launches, [8] photon_trace_kernel<continuation> launches.
  * [2],[3],[6]-[9] are only filled while profiling is on. */
 int cgrt_get_timings(cgrt_ctx *ctx, double ms[12]);
+/* Debug aid (the reference has none; it stands in for a memory checker): when the process runs with CGRT_GUARD=1 in its
+ * environment every device buffer of a context sits between two 4 KiB fences of a known byte pattern. Synchronises and returns in
+ * *damaged the number of fence bytes kernels have overwritten so far (released buffers included); 0 when the mode is off. */
+int cgrt_check_guards(cgrt_ctx *ctx, uint64_t *damaged);
 
 #ifdef __cplusplus
 }

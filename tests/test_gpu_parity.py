@@ -436,3 +436,14 @@ def test_photon_pass_with_bezier_object(gpu, oracle_lib):
         assert abs(a.mean() - b.mean()) <= 0.01 * b.mean()
         # pixels whose hitpoints are not on the vase see exactly the same photons except those that went through the vase
         assert np.median(np.abs(a - b) / np.maximum(b, 1e-9)) < 1e-3
+
+
+def test_no_out_of_bounds_writes_with_fenced_buffers():
+    """Every scene family, both accumulator modes and the two-stream pipeline with CGRT_GUARD=1: each device buffer sits between two
+    4 KiB fences and no kernel may have written into one (stands in for a memory checker, which the GPU pool does not offer)."""
+    import subprocess, sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    env = dict(os.environ, CGRT_GUARD="1")
+    r = subprocess.run([sys.executable, os.path.join(root, "tools", "sanitize_probe.py")], env=env, capture_output=True, text=True, timeout=900)
+    assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-2000:]
+    assert "guard mode 1 damaged fence bytes 0" in r.stdout
