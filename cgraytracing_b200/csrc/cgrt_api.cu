@@ -1028,11 +1028,14 @@ int cgrt_build_grid(cgrt_ctx *ctx) {
     size_t acc_bytes = (size_t)n * 4 * (ctx->cfg.accum_mode == 0 ? sizeof(double) : sizeof(float));
     {
         auto up = [](size_t b) { return (b + 255) & ~(size_t)255; };
-        size_t o_pre = 0, o_hot = o_pre + up((size_t)n * sizeof(float4)), o_f = o_hot + up((size_t)n * sizeof(HpHot));
+        size_t o_pre = 0, o_pren = o_pre + up((size_t)n * sizeof(float4)), o_pref = o_pren + up((size_t)n * sizeof(float4));
+        size_t o_hot = o_pref + up((size_t)n * sizeof(float4)), o_f = o_hot + up((size_t)n * sizeof(HpHot));
         size_t o_acc = o_f + up((size_t)n * 4 * sizeof(double)), total = o_acc + up(acc_bytes);
         char *slab;
         CKS(dalloc(ctx, &slab, total));
         ctx->A.pre = reinterpret_cast<float4 *>(slab + o_pre);
+        ctx->A.pre_n = reinterpret_cast<float4 *>(slab + o_pren);
+        ctx->A.pre_f = reinterpret_cast<float4 *>(slab + o_pref);
         ctx->A.hot = reinterpret_cast<HpHot *>(slab + o_hot);
         ctx->A.f = reinterpret_cast<double *>(slab + o_f);
         ctx->acc = slab + o_acc;
@@ -1176,11 +1179,11 @@ int cgrt_photon_pass(cgrt_ctx *ctx, uint64_t first, uint64_t count) {
             size_t want = (spans * 32 + CGRT_DEPOSIT_BLOCK - 1) / CGRT_DEPOSIT_BLOCK;
             unsigned int dblocks = (unsigned int)(want < (size_t)ctx->deposit_grid ? want : (size_t)ctx->deposit_grid);
             if (ctx->cfg.accum_mode == 0)
-                photon_deposit_kernel<0><<<dblocks, CGRT_DEPOSIT_BLOCK, 0, D>>>(P, B.rec, B.perm, B.nvalid, ctx->cell_start, ctx->A.pre, ctx->A.hot,
-                                                                                ctx->A.f, ctx->acc, ctx->d_ctr);
+                photon_deposit_kernel<0><<<dblocks, CGRT_DEPOSIT_BLOCK, 0, D>>>(P, B.rec, B.perm, B.nvalid, ctx->cell_start, ctx->A.pre, ctx->A.pre_n,
+                                                                                ctx->A.pre_f, ctx->A.hot, ctx->A.f, ctx->acc, ctx->d_ctr);
             else
-                photon_deposit_kernel<1><<<dblocks, CGRT_DEPOSIT_BLOCK, 0, D>>>(P, B.rec, B.perm, B.nvalid, ctx->cell_start, ctx->A.pre, ctx->A.hot,
-                                                                                ctx->A.f, ctx->acc, ctx->d_ctr);
+                photon_deposit_kernel<1><<<dblocks, CGRT_DEPOSIT_BLOCK, 0, D>>>(P, B.rec, B.perm, B.nvalid, ctx->cell_start, ctx->A.pre, ctx->A.pre_n,
+                                                                                ctx->A.pre_f, ctx->A.hot, ctx->A.f, ctx->acc, ctx->d_ctr);
             ctx->launches++;
         } else if (ctx->profiling) {
             CK(cudaEventRecord(e[2], D));

@@ -29,6 +29,16 @@ __device__ __forceinline__ float4 make_prefilter(double px, double py, double pz
     double b = (r + E) * (r + E) * (1.0 + 4e-6);
     return make_float4((float)px, (float)py, (float)pz, __double2float_ru(b));
 }
+// The same bound read the other way: a float squared distance <= (r - E)^2 (rounded down, negative when r <= E so that nothing
+// qualifies) proves the fp64 test dot(dd, dd) <= r2 of main.cpp:116 true. Stored next to the fp32 normal: {nx, ny, nz, (r - E)^2}.
+__device__ __forceinline__ float prefilter_inner(double px, double py, double pz, double r2) {
+    double r = sqrt(r2);
+    double m = fmax(fmax(fabs(px), fabs(py)), fabs(pz)) + r + 1.0;
+    double E = 4.5e-7 * m;
+    if (r <= E) return -1.0f;
+    double b = (r - E) * (r - E) * (1.0 - 4e-6);
+    return __double2float_rd(b);
+}
 
 struct PassParams {
     int width, height, max_depth, samples, use_dof;
@@ -206,6 +216,8 @@ __global__ void hp_extract_keys_kernel(const double *__restrict__ rec, unsigned 
 
 struct HpArrays {
     float4 *pre;           // fp32 prefilter {x, y, z, (r+E)^2} read per candidate
+    float4 *pre_n;         // fp32 accept filter {nx, ny, nz, (r-E)^2}
+    float4 *pre_f;         // fp32 copy of f {fx, fy, fz, 0} (float-accumulator mode deposits from it)
     HpHot *hot;            // pos, r2, normal (exact test)
     double *f;             // [n][4] f*adj (+pad)
     double *flux;          // [n][4] tau (+pad)
@@ -225,6 +237,8 @@ __global__ void hp_gather_sorted_kernel(const double *__restrict__ rec, const ui
     h.nx = r[3]; h.ny = r[4]; h.nz = r[5]; h.pad = 0.0;
     A.hot[k] = h;
     A.pre[k] = make_prefilter(h.px, h.py, h.pz, r2_init);
+    A.pre_n[k] = make_float4((float)h.nx, (float)h.ny, (float)h.nz, prefilter_inner(h.px, h.py, h.pz, r2_init));
+    A.pre_f[k] = make_float4((float)r[6], (float)r[7], (float)r[8], 0.f);
     A.f[4 * (size_t)k] = r[6]; A.f[4 * (size_t)k + 1] = r[7]; A.f[4 * (size_t)k + 2] = r[8]; A.f[4 * (size_t)k + 3] = 0.0;
     A.flux[4 * (size_t)k] = 0.0; A.flux[4 * (size_t)k + 1] = 0.0; A.flux[4 * (size_t)k + 2] = 0.0; A.flux[4 * (size_t)k + 3] = 0.0;
     A.cnt[k] = 0;
@@ -591,54 +605,134 @@ __device__ __forceinline__ double4 ldg4(const double4 *p) {  // 32 bytes of a de
     return make_double4(a.x, a.y, b.x, b.y);
 }
 
-struct HitShared {  // exact data of the 32 records of a warp's batch, structure of arrays (one 256-byte row per component)
+// What a warp keeps in shared memory about the 32 records of its batch (structure of arrays, one row per component).
+// ACC 0 (fp64 accumulators): the exact fp64 record, because every deposit is computed from the fp64 flux.
+// ACC 1 (float accumulators): only the fp32 copy and the slot of the record; the few pairs the fp32 filters cannot decide re-read the
+// record from the deposit table.
+template <int ACC>
+struct HitShared;
+template <>
+struct HitShared<0> {
     double v[9][32];  // pos.xyz, nrm.xyz, flux.xyz
+    float f[6][32];   // fp32 pos.xyz, nrm.xyz
+};
+template <>
+struct HitShared<1> {
+    float f[9][32];   // fp32 pos.xyz, nrm.xyz, flux.xyz
+    uint32_t src[32]; // slot of the record in the deposit table
 };
 
+struct ExactHit {  // the fp64 photon side of one pair
+    d3 X, nrm, flux;
+};
+__device__ __forceinline__ ExactHit exact_hit(const HitShared<0> &H, uint32_t hl, const DepositRec *) {
+    ExactHit e;
+    e.X = mk(H.v[0][hl], H.v[1][hl], H.v[2][hl]); e.nrm = mk(H.v[3][hl], H.v[4][hl], H.v[5][hl]); e.flux = mk(H.v[6][hl], H.v[7][hl], H.v[8][hl]);
+    return e;
+}
+__device__ __forceinline__ ExactHit exact_hit(const HitShared<1> &H, uint32_t hl, const DepositRec *__restrict__ rec) {
+    const double4 *r = reinterpret_cast<const double4 *>(rec + H.src[hl]);
+    double4 r0 = ldg4(r), r1 = ldg4(r + 1), r2 = ldg4(r + 2);
+    ExactHit e;
+    e.X = mk(r0.x, r0.y, r0.z); e.nrm = mk(r0.w, r1.x, r1.y); e.flux = mk(r1.z, r1.w, r2.x);
+    return e;
+}
+
 template <int ACC>
-__device__ __forceinline__ void deposit_exact(const HitShared &H, uint32_t hl, uint32_t hidx, const HpHot *__restrict__ hot,
-                                              const double *__restrict__ hp_f, void *__restrict__ acc, unsigned int &ndep) {
+__device__ __forceinline__ void deposit_add(void *__restrict__ acc, uint32_t hidx, d3 cc) {
+    if (ACC == 0) {
+        double *ap = reinterpret_cast<double *>(acc) + 4 * (size_t)hidx;
+        atomicAdd(ap, cc.x); atomicAdd(ap + 1, cc.y); atomicAdd(ap + 2, cc.z); atomicAdd(ap + 3, 1.0);
+    } else {
+        float *ap = reinterpret_cast<float *>(acc) + 4 * (size_t)hidx;
+        asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(ap), "f"((float)cc.x), "f"((float)cc.y), "f"((float)cc.z), "f"(1.0f)
+                     : "memory");
+    }
+}
+
+// The reference's test and deposit in fp64 (main.cpp:116-122) for one pair, from the 64-byte exact record of the hitpoint.
+template <int ACC>
+__device__ __forceinline__ void deposit_exact(const ExactHit &e, uint32_t hidx, const HpHot *__restrict__ hot, const double *__restrict__ hp_f,
+                                              void *__restrict__ acc, unsigned int &ndep) {
     const double2 *hp = reinterpret_cast<const double2 *>(hot + hidx);
+    const double2 *fp = reinterpret_cast<const double2 *>(hp_f + 4 * (size_t)hidx);
     double2 a0 = __ldg(hp), a1 = __ldg(hp + 1), b0 = __ldg(hp + 2), b1 = __ldg(hp + 3);
-    d3 X = mk(H.v[0][hl], H.v[1][hl], H.v[2][hl]), nrm = mk(H.v[3][hl], H.v[4][hl], H.v[5][hl]);
+    double2 f0 = __ldg(fp), f1 = __ldg(fp + 1);
     d3 hpos = mk(a0.x, a0.y, a1.x);
     double r2 = a1.y;
     d3 hn = mk(b0.x, b0.y, b1.x);
-    d3 dd = hpos - X;
-    if ((dot(hn, nrm) > CGRT_EPS) && (dot(dd, dd) <= r2)) {  // main.cpp:116
-        const double2 *fp = reinterpret_cast<const double2 *>(hp_f + 4 * (size_t)hidx);
-        double2 f0 = __ldg(fp), f1 = __ldg(fp + 1);
-        d3 flux = mk(H.v[6][hl], H.v[7][hl], H.v[8][hl]);
-        d3 cc = (mk(f0.x, f0.y, f1.x) * flux) * (1.0 / CGRT_PI);  // f.mul(flux) * (1/PI), main.cpp:122
+    d3 dd = hpos - e.X;
+    if ((dot(hn, e.nrm) > CGRT_EPS) && (dot(dd, dd) <= r2)) {  // main.cpp:116
+        d3 cc = (mk(f0.x, f0.y, f1.x) * e.flux) * (1.0 / CGRT_PI);  // f.mul(flux) * (1/PI), main.cpp:122
+        deposit_add<ACC>(acc, hidx, cc);
+        ndep++;
+    }
+}
+
+// One pair that passed the prefilter. Its outcome is decided in fp32 from shared memory whenever the rounding bounds allow it:
+//   distance   s = |fl(hp) - fl(X)|^2 <= (r - E)^2 proves dot(dd, dd) <= r2 (prefilter_inner); the prefilter already had s <= (r + E)^2
+//   normals    |fl-dot - dot| <= 5 * 2^-24 * sum |hn_i * nrm_i| (two input roundings and the float evaluation); 1e-6 * sum + 1e-9
+//              is the margin used, on either side of CGRT_EPS
+// A pair both filters accept is deposited without touching the hitpoint's exact record (float accumulators: from the fp32 copy of f in
+// shared memory; fp64 accumulators: f from global, flux from the shared fp64 record — the deposited value is the reference's).
+// A pair the normal filter rejects is dropped. Only pairs in the thin shells in between (about 1e-3 of them) take the fp64 path.
+template <int ACC>
+__device__ __forceinline__ void deposit_pair(const HitShared<ACC> &H, uint32_t hl, uint32_t hidx, float4 q, float4 qn, float4 qf,
+                                             const DepositRec *__restrict__ rec, const HpHot *__restrict__ hot, const double *__restrict__ hp_f,
+                                             void *__restrict__ acc, unsigned int &ndep) {
+    const float ddx = q.x - H.f[0][hl], ddy = q.y - H.f[1][hl], ddz = q.z - H.f[2][hl];
+    const float s = fmaf(ddz, ddz, fmaf(ddy, ddy, ddx * ddx));
+    const float nx = H.f[3][hl], ny = H.f[4][hl], nz = H.f[5][hl];
+    const float dn = fmaf(qn.z, nz, fmaf(qn.y, ny, qn.x * nx));
+    const float sn = fmaf(fabsf(qn.z), fabsf(nz), fmaf(fabsf(qn.y), fabsf(ny), fabsf(qn.x * nx)));
+    const float mg = fmaf(1e-6f, sn, 1e-9f);
+    const float eps = (float)CGRT_EPS;
+    if (dn < eps - mg) return;  // the normal test fails whatever the distance
+    if (s <= qn.w && dn > eps + mg) {
         if (ACC == 0) {
-            double *ap = reinterpret_cast<double *>(acc) + 4 * (size_t)hidx;
-            atomicAdd(ap, cc.x); atomicAdd(ap + 1, cc.y); atomicAdd(ap + 2, cc.z); atomicAdd(ap + 3, 1.0);
+            const double2 *fp = reinterpret_cast<const double2 *>(hp_f + 4 * (size_t)hidx);
+            double2 f0 = __ldg(fp), f1 = __ldg(fp + 1);
+            const HitShared<0> &H0 = reinterpret_cast<const HitShared<0> &>(H);
+            d3 cc = (mk(f0.x, f0.y, f1.x) * mk(H0.v[6][hl], H0.v[7][hl], H0.v[8][hl])) * (1.0 / CGRT_PI);
+            deposit_add<0>(acc, hidx, cc);
         } else {
+            const HitShared<1> &H1 = reinterpret_cast<const HitShared<1> &>(H);
+            const float ipi = (float)(1.0 / CGRT_PI);
             float *ap = reinterpret_cast<float *>(acc) + 4 * (size_t)hidx;
-            asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(ap), "f"((float)cc.x), "f"((float)cc.y), "f"((float)cc.z), "f"(1.0f)
+            asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(ap), "f"((qf.x * H1.f[6][hl]) * ipi), "f"((qf.y * H1.f[7][hl]) * ipi),
+                         "f"((qf.z * H1.f[8][hl]) * ipi), "f"(1.0f)
                          : "memory");
         }
         ndep++;
+        return;
     }
+    deposit_exact<ACC>(exact_hit(H, hl, rec), hidx, hot, hp_f, acc, ndep);
 }
 
 template <int ACC>
 __global__ void __launch_bounds__(CGRT_DEPOSIT_BLOCK) photon_deposit_kernel(const __grid_constant__ PassParams P, const DepositRec *__restrict__ rec,
                                                                             const uint32_t *__restrict__ perm, const uint32_t *__restrict__ n_valid,
                                                                             const uint32_t *__restrict__ cell_start,
-                                                                            const float4 *__restrict__ pre, const HpHot *__restrict__ hot,
+                                                                            const float4 *__restrict__ pre, const float4 *__restrict__ pre_n,
+                                                                            const float4 *__restrict__ pre_f, const HpHot *__restrict__ hot,
                                                                             const double *__restrict__ hp_f, void *__restrict__ acc, Counters *ctr) {
-    // per warp: 64 staged candidates (prefilter record + hitpoint index) and the queue of (record, hitpoint) pairs that
-    // passed the prefilter
-    __shared__ float4 cpre_all[CGRT_DEPOSIT_BLOCK / 32][64];
-    __shared__ uint32_t cidx_all[CGRT_DEPOSIT_BLOCK / 32][64];
-    __shared__ uint2 queue_all[CGRT_DEPOSIT_BLOCK / 32][64];
-    __shared__ HitShared hit_all[CGRT_DEPOSIT_BLOCK / 32];
+    // per warp: 64 staged candidates (fp32 filter records + hitpoint index) and the queue of (record, candidate) pairs that passed
+    // the prefilter
+    constexpr int NW = CGRT_DEPOSIT_BLOCK / 32;
+    __shared__ float4 cpre_all[NW][64];
+    __shared__ float4 cnrm_all[NW][64];
+    __shared__ float4 cf_all[ACC == 1 ? NW : 1][64];
+    __shared__ uint32_t cidx_all[NW][64];
+    __shared__ uint32_t queue_all[NW][64];
+    __shared__ HitShared<ACC> hit_all[NW];
     const int lane = threadIdx.x & 31;
-    HitShared &H = hit_all[threadIdx.x >> 5];
-    float4 *cpre = cpre_all[threadIdx.x >> 5];
-    uint32_t *cidx = cidx_all[threadIdx.x >> 5];
-    uint2 *queue = queue_all[threadIdx.x >> 5];
+    const int wib = threadIdx.x >> 5;
+    HitShared<ACC> &H = hit_all[wib];
+    float4 *cpre = cpre_all[wib];
+    float4 *cnrm = cnrm_all[wib];
+    float4 *cf = cf_all[ACC == 1 ? wib : 0];
+    uint32_t *cidx = cidx_all[wib];
+    uint32_t *queue = queue_all[wib];
     const unsigned int lt = (1u << lane) - 1u;
     const size_t warp = ((size_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     const size_t nwarps = ((size_t)gridDim.x * blockDim.x) >> 5;
@@ -648,6 +742,14 @@ __global__ void __launch_bounds__(CGRT_DEPOSIT_BLOCK) photon_deposit_kernel(cons
     int qn = 0;
     const size_t n_slots = (size_t)__ldg(n_valid);
     if (blockIdx.x == 0 && threadIdx.x == 0) atomicAdd(&ctr->gathered_hits, (unsigned long long)n_slots);
+    // one exact step: 32 queued pairs (fewer at the end of a stage), one per lane
+    auto step = [&](int first, int count) {
+        if (lane < count) {
+            const uint32_t e = queue[first + lane];
+            const uint32_t hl = e & 31u, b = e >> 8;
+            deposit_pair<ACC>(H, hl, cidx[b], cpre[b], cnrm[b], ACC == 1 ? cf[b] : make_float4(0.f, 0.f, 0.f, 0.f), rec, hot, hp_f, acc, ndep);
+        }
+    };
     for (size_t span = warp * CGRT_DEPOSIT_SPAN; span < n_slots; span += nwarps * CGRT_DEPOSIT_SPAN) {
         const size_t span_end = span + CGRT_DEPOSIT_SPAN < n_slots ? span + CGRT_DEPOSIT_SPAN : n_slots;
         for (size_t base = span; base < span_end; base += 32) {
@@ -659,13 +761,22 @@ __global__ void __launch_bounds__(CGRT_DEPOSIT_BLOCK) photon_deposit_kernel(cons
             if (valid) {
                 const uint32_t src = __ldcs(perm + j);
                 const double4 *r = reinterpret_cast<const double4 *>(rec + src);
-                double4 r0 = ldg4(r), r1 = ldg4(r + 1), r2 = ldg4(r + 2);  // streamed once: the exact data goes to shared memory
+                double4 r0 = ldg4(r), r1 = ldg4(r + 1), r2 = ldg4(r + 2);  // streamed once
                 hx = (float)r0.x; hy = (float)r0.y; hz = (float)r0.z;
                 long long cxy = __double_as_longlong(r2.y);
                 ix = (int)(uint32_t)cxy; iy = (int)(uint32_t)(cxy >> 32); iz = (int)(uint32_t)__double_as_longlong(r2.z);
-                H.v[0][lane] = r0.x; H.v[1][lane] = r0.y; H.v[2][lane] = r0.z;
-                H.v[3][lane] = r0.w; H.v[4][lane] = r1.x; H.v[5][lane] = r1.y;
-                H.v[6][lane] = r1.z; H.v[7][lane] = r1.w; H.v[8][lane] = r2.x;
+                H.f[0][lane] = hx; H.f[1][lane] = hy; H.f[2][lane] = hz;
+                H.f[3][lane] = (float)r0.w; H.f[4][lane] = (float)r1.x; H.f[5][lane] = (float)r1.y;
+                if (ACC == 0) {
+                    HitShared<0> &H0 = reinterpret_cast<HitShared<0> &>(H);
+                    H0.v[0][lane] = r0.x; H0.v[1][lane] = r0.y; H0.v[2][lane] = r0.z;
+                    H0.v[3][lane] = r0.w; H0.v[4][lane] = r1.x; H0.v[5][lane] = r1.y;
+                    H0.v[6][lane] = r1.z; H0.v[7][lane] = r1.w; H0.v[8][lane] = r2.x;
+                } else {
+                    HitShared<1> &H1 = reinterpret_cast<HitShared<1> &>(H);
+                    H1.f[6][lane] = (float)r1.z; H1.f[7][lane] = (float)r1.w; H1.f[8][lane] = (float)r2.x;
+                    H1.src[lane] = src;
+                }
             }
             __syncwarp();
             unsigned int remaining = __ballot_sync(0xffffffffu, valid);
@@ -705,8 +816,8 @@ __global__ void __launch_bounds__(CGRT_DEPOSIT_BLOCK) photon_deposit_kernel(cons
                         const uint32_t c = c0 + 32 * h + lane;
                         int lo = 0;  // owner bucket of candidate c = last lane < 27 whose excl <= c (shuffle binary search)
 #pragma unroll
-                        for (int step = 16; step >= 1; step >>= 1) {
-                            int probe = lo + step;
+                        for (int step_ = 16; step_ >= 1; step_ >>= 1) {
+                            int probe = lo + step_;
                             uint32_t e = __shfl_sync(0xffffffffu, excl, probe & 31);
                             if (probe < 27 && e <= c) lo = probe;
                         }
@@ -714,10 +825,12 @@ __global__ void __launch_bounds__(CGRT_DEPOSIT_BLOCK) photon_deposit_kernel(cons
                         const uint32_t b_lo = __shfl_sync(0xffffffffu, beg, lo);
                         bool keep = false;
                         uint32_t hidx = 0;
-                        float4 q = make_float4(0.f, 0.f, 0.f, -1.f);
+                        float4 q = make_float4(0.f, 0.f, 0.f, -1.f), q_n = q, q_f = q;
                         if (c < total) {
                             hidx = b_lo + (c - e_lo);
                             q = __ldg(pre + hidx);
+                            q_n = __ldg(pre_n + hidx);
+                            if (ACC == 1) q_f = __ldg(pre_f + hidx);
                             const float ex = fmaxf(fmaxf(bx0 - bm - q.x, q.x - (bx0 + bw + bm)), 0.f);
                             const float ey = fmaxf(fmaxf(by0 - bm - q.y, q.y - (by0 + bw + bm)), 0.f);
                             const float ez = fmaxf(fmaxf(bz0 - bm - q.z, q.z - (bz0 + bw + bm)), 0.f);
@@ -727,6 +840,8 @@ __global__ void __launch_bounds__(CGRT_DEPOSIT_BLOCK) photon_deposit_kernel(cons
                         if (keep) {
                             const int at = nc + __popc(km & lt);
                             cpre[at] = q;
+                            cnrm[at] = q_n;
+                            if (ACC == 1) cf[at] = q_f;
                             cidx[at] = hidx;
                         }
                         nc += __popc(km);
@@ -760,28 +875,23 @@ __global__ void __launch_bounds__(CGRT_DEPOSIT_BLOCK) photon_deposit_kernel(cons
                         if (m_lo) { b = __ffs(m_lo) - 1; m_lo &= m_lo - 1; }
                         else if (m_hi) { b = 32 + __ffs(m_hi) - 1; m_hi &= m_hi - 1; }
                         const unsigned int pm = __ballot_sync(0xffffffffu, has);
-                        if (has) queue[qn + __popc(pm & lt)] = make_uint2((uint32_t)lane, cidx[b]);
+                        if (has) queue[qn + __popc(pm & lt)] = (uint32_t)lane | ((uint32_t)b << 8);
                         qn += __popc(pm);
                         npair += (lane == 0) ? (unsigned int)__popc(pm) : 0u;
                         if (qn >= 32) {
                             __syncwarp();
-                            const uint2 pr = queue[qn - 32 + lane];
                             qn -= 32;
-                            deposit_exact<ACC>(H, pr.x, pr.y, hot, hp_f, acc, ndep);
+                            step(qn, 32);
                             __syncwarp();
                         }
                     }
-                    __syncwarp();  // cpre / cidx are restaged next
+                    // the queue refers to the staged candidates: empty it before they are restaged
+                    __syncwarp();
+                    step(0, qn);
+                    qn = 0;
+                    __syncwarp();
                 }
             }
-            // the queue refers to this batch's shared-memory hit data: flush it before the next batch overwrites them
-            __syncwarp();
-            if (lane < qn) {
-                const uint2 pr = queue[lane];
-                deposit_exact<ACC>(H, pr.x, pr.y, hot, hp_f, acc, ndep);
-            }
-            qn = 0;
-            __syncwarp();
         }
     }
     // counters: warp-reduce then one atomic per warp
@@ -890,6 +1000,7 @@ __global__ void round_update_kernel(unsigned int n, double alpha, HpArrays A, vo
         hh.r2 *= g;
         A.hot[k].r2 = hh.r2;
         A.pre[k] = make_prefilter(hh.px, hh.py, hh.pz, hh.r2);
+        A.pre_n[k].w = prefilter_inner(hh.px, hh.py, hh.pz, hh.r2);
         A.cnt[k] = cnt + (int)m;
     }
 }
