@@ -825,6 +825,12 @@ int cgrt_commit_scene(cgrt_ctx *ctx) {
     }
     S.nbvh = nbvh;
     S.nbez = nbez;
+    S.nplane = S.nsphere = S.ndeferred = 0;
+    for (int i = 0; i < S.nobj; i++) {
+        if (S.obj[i].kind == OBJ_PLANE) S.plane_ix[S.nplane++] = (unsigned char)i;
+        if (S.obj[i].kind == OBJ_SPHERE) S.sphere_ix[S.nsphere++] = (unsigned char)i;
+        if (S.obj[i].bvh >= 0 || S.obj[i].kind == OBJ_BEZIER) S.deferred_ix[S.ndeferred++] = (unsigned char)i;
+    }
     for (double *h : heights) CKS(dfree(ctx, h));
     ctx->committed = true;
     return CGRT_OK;

@@ -205,6 +205,10 @@ struct BezDev {
 };
 struct SceneDev {
     int nobj, nbvh, ntex, nbez;
+    // object indices by class, each list ascending (filled by cgrt_commit_scene): the closest-hit loop is the lexicographic minimum
+    // of (len, index), so the classes can be walked separately — planes three at a time for instruction-level parallelism
+    int nplane, nsphere, ndeferred;
+    unsigned char plane_ix[CGRT_MAX_OBJECTS], sphere_ix[CGRT_MAX_OBJECTS], deferred_ix[CGRT_MAX_OBJECTS];
     ObjDev obj[CGRT_MAX_OBJECTS];
     BvhDev bvh[CGRT_MAX_BVH];
     TexDev tex[CGRT_MAX_TEX];
@@ -565,28 +569,43 @@ struct HitAcc {
 
 // phase 1: the cheap analytic primitives of one ray (planes, spheres), in object order. Meshes, displaced floors and Bezier
 // surfaces are "deferred objects": phase 2 resolves them with the lanes that actually need them packed densely.
+__device__ __forceinline__ void plane_take(const SceneDev &S, int i, double len, HitAcc &A) {
+    if (len > 0 && len < A.nearest) {
+        const ObjDev &O = S.obj[i];
+        A.id = i; A.nearest = len; A.nrm = mk(O.b[0], O.b[1], O.b[2]); A.prim = -1;
+    }
+}
 __device__ __forceinline__ void analytic_phase(const SceneDev &S, d3 o, d3 d, HitAcc &A) {
     A.nearest = CGRT_INF; A.id = -1; A.prim = -1; A.nrm = mk(0, 0, 0);
-    for (int i = 0; i < S.nobj; i++) {
+    // planes (objects.h:505-524; the displaced mesh of a bump plane is a phase-2 candidate), ascending index, strict <: the first of
+    // several planes at the same distance keeps the hit, as in the reference's loop. Three independent quotients are in flight at a time.
+    int k = 0;
+    for (; k + 3 <= S.nplane; k += 3) {
+        const int i0 = S.plane_ix[k], i1 = S.plane_ix[k + 1], i2 = S.plane_ix[k + 2];
+        const double l0 = plane_len(S.obj[i0], o, d), l1 = plane_len(S.obj[i1], o, d), l2 = plane_len(S.obj[i2], o, d);
+        plane_take(S, i0, l0, A); plane_take(S, i1, l1, A); plane_take(S, i2, l2, A);
+    }
+    for (; k < S.nplane; k++) {
+        const int i = S.plane_ix[k];
+        plane_take(S, i, plane_len(S.obj[i], o, d), A);
+    }
+    // spheres (objects.h:45-68) after the planes: a sphere at exactly the distance of the holder wins iff it precedes it in the object list
+    for (k = 0; k < S.nsphere; k++) {
+        const int i = S.sphere_ix[k];
         const ObjDev &O = S.obj[i];
-        if (O.kind == OBJ_PLANE) {  // objects.h:505-524 (the displaced mesh of a bump plane is a phase-2 candidate)
-            double len = plane_len(O, o, d);
-            if (len > 0 && len < A.nearest) { A.id = i; A.nearest = len; A.nrm = mk(O.b[0], O.b[1], O.b[2]); A.prim = -1; }
-        } else if (O.kind == OBJ_SPHERE) {  // objects.h:45-68
-            d3 l = mk(O.a[0], O.a[1], O.a[2]) - o;
-            double tca = dot(l, d);
-            double l2 = dot(l, l);
-            if (!(tca < 0 && l2 > O.r2)) {
-                double d2 = dot(l, l) - tca * tca;
-                if (!(d2 > O.r2)) {
-                    double thc = sqrt(O.r2 - d2);
-                    double t0 = tca - thc, t1 = tca + thc;
-                    double len = (t0 < 0) ? t1 : t0;
-                    if (len < A.nearest) {
-                        d3 p = o + d * len;
-                        A.id = i; A.nearest = len; A.prim = -1;
-                        A.nrm = normalize(p - mk(O.a[0], O.a[1], O.a[2]));
-                    }
+        d3 l = mk(O.a[0], O.a[1], O.a[2]) - o;
+        double tca = dot(l, d);
+        double l2 = dot(l, l);
+        if (!(tca < 0 && l2 > O.r2)) {
+            double d2 = dot(l, l) - tca * tca;
+            if (!(d2 > O.r2)) {
+                double thc = sqrt(O.r2 - d2);
+                double t0 = tca - thc, t1 = tca + thc;
+                double len = (t0 < 0) ? t1 : t0;
+                if (len < A.nearest || (len == A.nearest && i < A.id)) {
+                    d3 p = o + d * len;
+                    A.id = i; A.nearest = len; A.prim = -1;
+                    A.nrm = normalize(p - mk(O.a[0], O.a[1], O.a[2]));
                 }
             }
         }

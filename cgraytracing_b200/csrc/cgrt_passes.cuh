@@ -482,9 +482,9 @@ __global__ void __launch_bounds__(CGRT_TRACE_BLOCK, CGRT_TRACE_MINB) photon_trac
         bool suspended = false;
         if (!done && mode != PH_RESOLVED) {
             analytic_phase(S, o, d, A);
-            for (int k = 0; k < S.nobj; k++) {
+            for (int k = 0; k < S.ndeferred; k++) {
                 double lim;
-                if (is_deferred(S.obj[k]) && deferred_wanted(S, k, o, d, A, lim)) { suspended = true; break; }
+                if (deferred_wanted(S, S.deferred_ix[k], o, d, A, lim)) { suspended = true; break; }
             }
         }
         {   // suspend in front of a mesh: compact into the next queue (warp ballot + one atomic per warp)
