@@ -569,7 +569,7 @@ int cgrt_create(int device, cgrt_ctx **out) {
     {
         int sms = 148, nb = 0;
         cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, device);
-        auto occ = [&](const void *k) { return (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, k, CGRT_TRACE_BLOCK, 0) == cudaSuccess && nb > 0) ? (unsigned int)(nb * sms) : 592u; };
+        auto occ = [&](const void *k) { return (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, k, CGRT_PHOTON_BLOCK, 0) == cudaSuccess && nb > 0) ? (unsigned int)(nb * sms) : 592u; };
         ctx->grid_first = occ((const void *)photon_trace_kernel<true>);
         ctx->grid_cont = occ((const void *)photon_trace_kernel<false>);
         if (const char *e = getenv("CGRT_PHOTON_CHUNK")) { long long c = atoll(e); if (c > 0) ctx->photon_chunk = (size_t)c; }  // tests: force multi-chunk passes
@@ -1136,10 +1136,10 @@ int cgrt_photon_pass(cgrt_ctx *ctx, uint64_t first, uint64_t count) {
         CK(cudaMemsetAsync(ctx->d_qcount + 2, 0, 6 * sizeof(unsigned int), T));
         unsigned int *qc = ctx->d_qcount + 2;
 #define LAUNCH_PT(F, GRID, QIN, NIN, QOUT, NOUT)                                                                                    \
-    photon_trace_kernel<F><<<GRID, CGRT_TRACE_BLOCK, 0, T>>>(ctx->S, P, base, (unsigned int)n, QIN, NIN, QOUT, NOUT, B.rec, B.keys, B.hist, \
+    photon_trace_kernel<F><<<GRID, CGRT_PHOTON_BLOCK, 0, T>>>(ctx->S, P, base, (unsigned int)n, QIN, NIN, QOUT, NOUT, B.rec, B.keys, B.hist, \
                                                              ctx->cull ? ctx->reach : nullptr, ctx->d_ctr)
         {
-            unsigned int want = nblk(n, CGRT_TRACE_BLOCK);
+            unsigned int want = nblk(n, CGRT_PHOTON_BLOCK);
             stamp(-1);
             LAUNCH_PT(true, (want < ctx->grid_first ? want : ctx->grid_first), nullptr, nullptr, ctx->pq[0], qc);
             stamp(9);

@@ -84,6 +84,9 @@ struct Counters {
 // main.cpp:252-254) whatever order the wavefront produced the hitpoints in.
 // =================================================================================================================
 #define CGRT_TRACE_BLOCK 128
+#ifndef CGRT_PHOTON_BLOCK
+#define CGRT_PHOTON_BLOCK 128   /* threads per block of photon_trace_kernel */
+#endif
 // minimum resident blocks per SM asked of ptxas for the photon kernels (register caps; tuned with A/B builds)
 #ifndef CGRT_TRACE_MINB
 #define CGRT_TRACE_MINB 1   /* 6 (80 registers) and 8 (64 registers, spills) were measured: no gain / slower */
@@ -417,14 +420,14 @@ __global__ void __launch_bounds__(128) photon_bezier_kernel(const __grid_constan
 enum { PH_NEED = 0, PH_FRESH = 1, PH_DIFFUSE = 2, PH_HAVE_RAY = 3, PH_RESOLVED = 4 };
 
 template <bool FIRST>
-__global__ void __launch_bounds__(CGRT_TRACE_BLOCK, CGRT_TRACE_MINB) photon_trace_kernel(const __grid_constant__ SceneDev S, const __grid_constant__ PassParams P,
+__global__ void __launch_bounds__(CGRT_PHOTON_BLOCK, CGRT_TRACE_MINB) photon_trace_kernel(const __grid_constant__ SceneDev S, const __grid_constant__ PassParams P,
                                                                         uint64_t first_index, unsigned int n, const PhotonState *__restrict__ qin,
                                                                         const unsigned int *__restrict__ n_in, PhotonState *__restrict__ qout,
                                                                         unsigned int *n_out, DepositRec *__restrict__ rec, uint32_t *__restrict__ keys,
                                                                         uint32_t *__restrict__ hist, const uint32_t *__restrict__ reach, Counters *ctr) {
     const unsigned int total = FIRST ? n : *n_in;
-    const unsigned int stride = gridDim.x * CGRT_TRACE_BLOCK;
-    unsigned int next = blockIdx.x * CGRT_TRACE_BLOCK + threadIdx.x;
+    const unsigned int stride = gridDim.x * CGRT_PHOTON_BLOCK;
+    unsigned int next = blockIdx.x * CGRT_PHOTON_BLOCK + threadIdx.x;
     unsigned int nseg = 0, nhit = 0;
     int mode = PH_NEED;
     d3 o = mk(0, 0, 0), d = mk(0, 0, 1), flux = mk(0, 0, 0), n_ff = mk(0, 0, 1);

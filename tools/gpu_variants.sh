@@ -1,4 +1,4 @@
-for v in A B A B; do
+for v in C A B; do
   if [ $v = base ]; then unset CGRT_LIB; else export CGRT_LIB=$PWD/gpurun_variants_$v.so; fi
   python bench.py --steps 3 --warmup 2 --cpu-photons 0 --e2e-rounds 0 > gpurun_out/bench_var_$v.json 2> gpurun_out/bench_var_$v.err
   python - <<PY
