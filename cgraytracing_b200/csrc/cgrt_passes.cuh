@@ -513,6 +513,12 @@ __global__ void __launch_bounds__(CGRT_PHOTON_BLOCK, CGRT_TRACE_MINB) photon_tra
         nseg += traced ? 1u : 0u;
         if (traced && A.id >= 0) {
             d3 X = o + d * A.nearest;  // main.cpp:68
+            // the cell of the hit and its word of the reach map first: the load is in flight while the surface colour (a texel fetch
+            // on the floor) and the normal are worked out
+            int ix, iy, iz;
+            cell_coord(X, P.celllength, P.inv_celllength, ix, iy, iz);
+            const uint32_t rh = reach_hash(ix, iy, iz);
+            const uint32_t rword = reach ? __ldg(reach + (rh >> 5)) : 0xffffffffu;
             d3 n_old = A.nrm;
             n_ff = A.nrm;
             bool into = true;
@@ -521,11 +527,8 @@ __global__ void __launch_bounds__(CGRT_PHOTON_BLOCK, CGRT_TRACE_MINB) photon_tra
             const int mat = S.obj[A.id].material;
             if (mat == MAT_DIFFUSE) {  // the 27-cell gather of main.cpp:103-125 runs in photon_deposit_kernel
                 const size_t slot = (size_t)depth * (size_t)n + (size_t)local;
-                int ix, iy, iz;
-                cell_coord(X, P.celllength, P.inv_celllength, ix, iy, iz);
                 nhit++;
-                bool reachable = true;
-                if (reach) { uint32_t h = reach_hash(ix, iy, iz); reachable = (__ldg(reach + (h >> 5)) >> (h & 31u)) & 1u; }
+                const bool reachable = (rword >> (rh & 31u)) & 1u;
                 if (reachable) {
                     double2 *r = reinterpret_cast<double2 *>(rec + slot);  // streamed: written once, read once by the deposit kernel
 #ifndef CGRT_EXP_NOREC
