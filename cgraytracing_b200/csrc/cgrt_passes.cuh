@@ -339,7 +339,9 @@ __device__ __forceinline__ uint32_t cell_bin(int ix, int iy, int iz) {
 // small register footprint). The winner of (analytic hit, mesh hits) is written back into the entry.
 // (Measured and rejected: a persistent form in which lanes whose traversal has ended take the next ray of the warp's share as soon as
 // 4/8/16 lanes are idle. Live lanes per instruction rose from 6-9 to 11.6, but the instruction count only fell by 14 % (loop and refill
-// overhead, 224 bytes of spills at 64 registers) and the issue rate dropped from 61 % to 47 %: 6.8-7.0 ms vs 5.7 ms per round.)
+// overhead, 224 bytes of spills at 64 registers) and the issue rate dropped from 61 % to 47 %: 6.8-7.0 ms vs 5.7 ms per round.
+// Also rejected: a warp-synchronous traversal that postpones leaves and tests the postponed triangles of 4/8/16 lanes together (the fp64
+// triangle test is 27 % of the instructions at 1.7 live lanes): 6.2-6.3 ms — the two ballots per node step cost more than the test saves.)
 template <bool COUNT>
 __global__ void __launch_bounds__(128, CGRT_TRAV_MINB) photon_traverse_kernel(const __grid_constant__ SceneDev S, PhotonState *__restrict__ q,
                                                               const unsigned int *__restrict__ n_in, TravCounters *tcg) {
