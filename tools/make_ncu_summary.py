@@ -1,0 +1,48 @@
+"""Write profiles/<tag>_ncu_summary.md from a launch list csv and an ncu --set full report (dev tool).
+usage: python tools/make_ncu_summary.py <tag> <launches.csv> <report.ncu-rep> <bench.json>"""
+import json, subprocess, sys, os
+tag, csvf, rep, benchf = sys.argv[1:5]
+here = os.path.dirname(os.path.abspath(__file__))
+run = lambda *a: subprocess.run(a, capture_output=True, text=True).stdout
+b = json.load(open(benchf))
+k = b["kernels"]
+sp = k["photon_trace_kernel"]["split_ms"]
+out = []
+out.append(f"# {tag} - ncu evidence, one B200, {b['config']['workload']} {b['config']['width']}x{b['config']['height']}, "
+           f"{b['config']['photons_per_gpu_per_step']} photons per round\n")
+out.append("Command under ncu: `python bench.py --steps 1 --warmup 1 --cpu-photons 0 --e2e-rounds 0` (the same command exited 0 without ncu immediately "
+           "before each pass), `--clock-control none`. Numbers printed by runs under ncu are not bench values; the bench line of the same code is "
+           f"`profiles/{tag}_bench.json` (un-profiled run: {b['value']/1e6:.1f} M photons/s, {b['ms_per_step']:.2f} ms per round).\n")
+out.append(f"## 1. Launch list of one round (profiles/{tag}_launches.csv)\n")
+out.append("CUDA-event split of the un-profiled bench run for comparison: " + ", ".join(f"{a} {v:.2f} ms" for a, v in sp.items()) +
+           f"; photon_deposit_kernel {k['photon_deposit_kernel']['seconds']*1e3:.2f} ms; counting sort {k['bin_scan+bin_scatter_kernel']['seconds']*1e3:.2f} ms; "
+           f"round_update_kernel {k['round_update_kernel']['seconds']*1e3:.2f} ms. ncu serialises launches and runs them cold, so the shares agree, not the absolutes.\n")
+tbl = run(sys.executable, os.path.join(here, "launch_table.py"), csvf).splitlines()
+# the last round of the run: from the last round_update before the final deposit back to the deposit
+last_dep = max(i for i, l in enumerate(tbl) if "photon_deposit_kernel" in l)
+start = max(i for i, l in enumerate(tbl[:last_dep]) if "photon_trace_kernel<1>" in l)
+out.append("```\n" + "\n".join(tbl[start:last_dep + 1]) + "\n```\n")
+out.append(f"## 2. Per-kernel metrics (`ncu --set full`, the 12 photon kernels of one round)\n")
+out.append("```\n" + run(sys.executable, os.path.join(here, "ncu_raw.py"), rep) + "```\n")
+out.append("## 3. Warp states (pc sampling) per kernel\n")
+out.append("```\n" + run(sys.executable, os.path.join(here, "ncu_stalls.py"), rep) + "```\n")
+out.append("## 4. Hot source lines (ncu --page source aggregated by tools/ncu_lines.py; first launch of each kernel)\n")
+for name in ("photon_deposit", "photon_traverse", "photon_trace"):
+    src = subprocess.run(f"ncu -i {rep} --page source --csv --print-source cuda,sass --kernel-name regex:{name} -c 1 2>/dev/null | {sys.executable} {here}/ncu_lines.py 16",
+                         shell=True, capture_output=True, text=True).stdout
+    out.append(f"### {name}\n```\n{src}```\n")
+out.append("""## 5. Reading
+
+* No kernel is bound by HBM (DRAM throughput <= 32 % of the measured copy peak) or by launch overhead (16 launches per ~22 ms round).
+* photon_trace_kernel (emission and continuation) is bound by dependent fp64 latency: 4 warps per scheduler (108 registers), 0.47 issue
+  slots per cycle, warp states `wait` + `short_scoreboard` + `long_scoreboard` ~ 65 %. Measured and found flat: block size 64/96/128,
+  register caps of 96/80/64, three plane quotients in flight (kept, -5 %).
+* photon_traverse_kernel is bound by divergence: 6-9 of 32 lanes live per instruction (one ray per lane, path lengths from 1 to hundreds
+  of nodes; the fp64 triangle test runs at 1.7 lanes). Three restructurings that raise the live-lane count (while-while, per-lane refill,
+  postponed leaf batches) were measured slower: the kernel's issue rate falls faster than its instruction count.
+* photon_deposit_kernel is close to issue-bound (0.66 issue slots per cycle, 29.7 of 32 lanes live, l1tex 80 %): the prefilter scan is
+  27 % of its instructions, the drain into the pair queue 23 %; the fp64 exact test left the profile when pairs started being decided
+  in fp32 from shared memory (line `deposit_pair`).
+""")
+open(f"profiles/{tag}_ncu_summary.md", "w").write("\n".join(out))
+print("wrote", f"profiles/{tag}_ncu_summary.md")
