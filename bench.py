@@ -162,7 +162,7 @@ def run_reference(args):
                                    f"(pinned bit-exact to the compiled reference), {threads} OpenMP threads"},
         "e2e": {"value": v, "unit": "photons/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }
-    print(json.dumps(line), flush=True)
+    emit_line(line)
 
 
 # ---------------------------------------------------------------------------------------------------------------------
@@ -350,7 +350,7 @@ def run_gpu(args):
         "roofline": roofline, "kernels": kernels, "cpu_baseline": cpu, "clocks": clocks, "e2e": e2e,
         "gpu_launches": int(c2["gpu_launches"] - c1["gpu_launches"]),
     }
-    print(json.dumps(line), flush=True)
+    emit_line(line)
     if world > 1:
         dist.destroy_process_group()
 
@@ -378,5 +378,39 @@ def main():
         run_gpu(args)
 
 
+class _QuietStdout:
+    """Everything native libraries print on fd 1 while the benchmark runs (NCCL's version banner, for one) goes to stderr, so that the
+    JSON line is the only thing on stdout."""
+
+    def __enter__(self):
+        sys.stdout.flush()
+        self.saved = os.dup(1)
+        os.dup2(2, 1)
+        return self
+
+    def emit(self, text):
+        sys.stdout.flush()
+        os.dup2(self.saved, 1)
+        print(text, flush=True)
+        os.dup2(2, 1)
+
+    def __exit__(self, *a):
+        sys.stdout.flush()
+        os.dup2(self.saved, 1)
+        os.close(self.saved)
+
+
+_OUT = None
+
+
+def emit_line(line):
+    text = json.dumps(line)
+    if _OUT is not None:
+        _OUT.emit(text)
+    else:
+        print(text, flush=True)
+
+
 if __name__ == "__main__":
-    main()
+    with _QuietStdout() as _OUT:
+        main()
