@@ -820,6 +820,7 @@ int cgrt_commit_scene(cgrt_ctx *ctx) {
             Z.box[4] = max_z + ho.a[2]; Z.box[5] = -max_z + ho.a[2];
             double rz = Z.cp[Z.ncp - 1][2];
             Z.umin_r2 = rz * rz;
+            bez_binomials(Z.ncp, Z.C, Z.Cm);
             O.aux = nbez++;
         }
     }

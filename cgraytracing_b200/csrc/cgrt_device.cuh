@@ -202,6 +202,7 @@ struct BezDev {
     double pos[3];
     double box[6];          // xmax,xmin,ymax,ymin,zmax,zmin (bezier.h:64-69)
     double umin_r2;         // cap radius^2 = cp[last].z^2 (bezier.h:277)
+    double C[CGRT_MAX_CP], Cm[CGRT_MAX_CP];  // binomial rows n and n-1 (bez_binomials; filled by cgrt_commit_scene)
 };
 struct SceneDev {
     int nobj, nbvh, ntex, nbez;
@@ -396,12 +397,18 @@ __device__ __forceinline__ bool box_any_face_hit(const double *b, d3 o, d3 d) { 
 // which is NOT the derivative n * (B(n-1,i-1) - B(n-1,i)) of the Bernstein basis (the correct form is commented out at
 // bezier.h:39). The reference's Newton Jacobian and its surface normals are built from this quantity, so the picture
 // depends on it and it is reproduced as is (gradP(0) = (0,32,-8), not 3*(P1-P0) = (0,36,0)).
-__device__ __forceinline__ void bez_eval(const BezDev &Z, double u, d3 &P, d3 &dP) {
-    int n = Z.ncp - 1;
-    double C[CGRT_MAX_CP], Cm[CGRT_MAX_CP];  // binomial rows n and n-1
+// The two binomial rows, by the recurrence every evaluation used to repeat (2n fp64 divisions per Newton iteration); computed once per
+// surface on the host with the same IEEE operations.
+__host__ __device__ inline void bez_binomials(int ncp, double *C, double *Cm) {
+    int n = ncp - 1;
+    for (int i = 0; i < CGRT_MAX_CP; i++) { C[i] = 0.0; Cm[i] = 0.0; }
     C[0] = 1.0; Cm[0] = 1.0;
     for (int i = 1; i <= n; i++) C[i] = C[i - 1] * (double)(n - i + 1) / (double)i;
     for (int i = 1; i <= n - 1; i++) Cm[i] = Cm[i - 1] * (double)(n - i) / (double)i;
+}
+__device__ __forceinline__ void bez_eval(const BezDev &Z, double u, d3 &P, d3 &dP) {
+    int n = Z.ncp - 1;
+    const double *C = Z.C, *Cm = Z.Cm;
     double pu[CGRT_MAX_CP], pv[CGRT_MAX_CP];
     pu[0] = 1.0; pv[0] = 1.0;
     for (int i = 1; i <= n; i++) { pu[i] = pu[i - 1] * u; pv[i] = pv[i - 1] * (1.0 - u); }
@@ -417,10 +424,9 @@ __device__ __forceinline__ void bez_eval(const BezDev &Z, double u, d3 &P, d3 &d
     }
 }
 
-__device__ __forceinline__ d3 bez_F(const BezDev &Z, d3 par, d3 o, d3 d, d3 &P, d3 &dP) {  // bezier.h:144-149
+__device__ __forceinline__ d3 bez_F(const BezDev &Z, d3 par, d3 o, d3 d, d3 &P, d3 &dP, double &s, double &c) {  // bezier.h:144-149
     bez_eval(Z, par.y, P, dP);
-    double s, c;
-    sincos(par.z, &s, &c);
+    sincos(par.z, &s, &c);  // handed back: the Jacobian of the next Newton step needs the same pair
     d3 surf = mk(P.z * s, P.y, P.z * c);
     return o + d * par.x - mk(Z.pos[0], Z.pos[1], Z.pos[2]) - surf;
 }
@@ -441,12 +447,11 @@ __device__ __forceinline__ bool bezier_newton_seed(const BezDev &Z, d3 o, d3 d, 
     double theta = (pt.z < 0) ? 3.14159265 + atan(pt.x / pt.z) : atan(pt.x / pt.z);
     d3 par = mk(t0, u0, theta);
     d3 P, dP;
-    d3 F = bez_F(Z, par, o, d, P, dP);
+    double s, c;
+    d3 F = bez_F(Z, par, o, d, P, dP, s, c);
     int iter = 0;
     while (sqrt(dot(F, F)) > 1e-6 && iter < 100) {  // bezier.h:170
         iter++;
-        double s, c;
-        sincos(par.z, &s, &c);
         // Jacobian columns (bezier.h:150-162)
         d3 a = d;
         d3 b = mk(-s * dP.z, -dP.y, -c * dP.z);
@@ -454,7 +459,7 @@ __device__ __forceinline__ bool bezier_newton_seed(const BezDev &Z, d3 o, d3 d, 
         double D = det3(a, b, cc);
         if (D < 1e-4 && D > -1e-4) {  // vec3.h:105: singular -> the reference jitters; we nudge deterministically
             par = mk(par.x + 0.037, par.y + 0.029 * ((iter & 1) ? 1 : -1), par.z + 0.041);
-            F = bez_F(Z, par, o, d, P, dP);
+            F = bez_F(Z, par, o, d, P, dP, s, c);
             continue;
         }
         // inverse (vec3.h:109-117) applied to F (vec3.h:99-101)
@@ -463,13 +468,11 @@ __device__ __forceinline__ bool bezier_newton_seed(const BezDev &Z, d3 o, d3 d, 
         d3 rc = mk((b.x * cc.y - cc.x * b.y) / D, (cc.x * a.y - cc.y * a.x) / D, (a.x * b.y - a.y * b.x) / D);
         d3 step = ra * F.x + rb * F.y + rc * F.z;
         par = par - step;
-        F = bez_F(Z, par, o, d, P, dP);
+        F = bez_F(Z, par, o, d, P, dP, s, c);
     }
     if (!(sqrt(dot(F, F)) < 1e-4 && par.x > 0 && par.y <= 1 && par.y >= 0)) return false;  // bezier.h:257
     t_out = par.x;
     d3 g = normalize(dP);  // bezier.h:215-224
-    double s, c;
-    sincos(par.z, &s, &c);
     nrm_out = mk(g.y * s, -g.z, g.y * c);
     return true;
 }
