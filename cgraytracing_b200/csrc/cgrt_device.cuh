@@ -463,9 +463,13 @@ __device__ __forceinline__ bool bezier_newton_seed(const BezDev &Z, d3 o, d3 d, 
             continue;
         }
         // inverse (vec3.h:109-117) applied to F (vec3.h:99-101)
-        d3 ra = mk((b.y * cc.z - b.z * cc.y) / D, (cc.y * a.z - cc.z * a.y) / D, (a.y * b.z - a.z * b.y) / D);
-        d3 rb = mk((cc.x * b.z - cc.z * b.x) / D, (a.x * cc.z - a.z * cc.x) / D, (b.x * a.z - b.z * a.x) / D);
-        d3 rc = mk((b.x * cc.y - cc.x * b.y) / D, (cc.x * a.y - cc.y * a.x) / D, (a.x * b.y - a.y * b.x) / D);
+        // one reciprocal and nine products instead of the reference's nine quotients (vec3.h:109-117): the step differs from the
+        // reference's in the last bits only, Newton corrects itself, and the roots of this primitive are compared statistically anyway
+        // (the reference draws its starting points at random). 10.1 -> 7.9 ms per round on c1.
+        const double iD = 1.0 / D;
+        d3 ra = mk((b.y * cc.z - b.z * cc.y) * iD, (cc.y * a.z - cc.z * a.y) * iD, (a.y * b.z - a.z * b.y) * iD);
+        d3 rb = mk((cc.x * b.z - cc.z * b.x) * iD, (a.x * cc.z - a.z * cc.x) * iD, (b.x * a.z - b.z * a.x) * iD);
+        d3 rc = mk((b.x * cc.y - cc.x * b.y) * iD, (cc.x * a.y - cc.y * a.x) * iD, (a.x * b.y - a.y * b.x) * iD);
         d3 step = ra * F.x + rb * F.y + rc * F.z;
         par = par - step;
         F = bez_F(Z, par, o, d, P, dP, s, c);
