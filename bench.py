@@ -273,7 +273,12 @@ def run_gpu(args):
     dt = lambda k: (tp1[k] - tp0[k]) * 1e-3
     t_trace, t_dep, t_upd, t_sort = dt("photon_trace"), dt("photon_deposit"), dt("update"), dt("deposit_sort")
     t_emit, t_trav, t_cont = dt("trace_emit"), dt("trace_traverse"), dt("trace_continue")
-    n_chunks = (P + (16 << 20) - 1) // (16 << 20)  # chunks per round (cgrt_ctx::photon_chunk)
+    # chunks per round: the library takes as many photons per trace launch as fit in 60 % of the device memory, at most 128 Mi (cgrt_photon_pass)
+    per_photon = cfg.max_depth * (96 + 8) * (2 if args.overlap else 1) + 2 * 128
+    chunk = min(128 << 20, max(1 << 20, ((torch.cuda.mem_get_info(local)[1] // 10 * 6) // per_photon) & ~((1 << 20) - 1)))
+    if os.environ.get("CGRT_PHOTON_CHUNK"):
+        chunk = int(os.environ["CGRT_PHOTON_CHUNK"])
+    n_chunks = (P + chunk - 1) // chunk
     bytes_trace = seg * (B_SEGMENT + B_NODE * per_seg_nodes + B_TRI * per_seg_tris)
     bytes_dep = gathered * B_CELLS + cand * B_CAND + dep * B_DEP
     # DRAM bytes per round from the committed ncu --set full capture of this command line (profiles/r01_final_ncu_summary.md); only

@@ -73,7 +73,7 @@ void arena_give(int device, size_t bytes, void *p) {
     std::lock_guard<std::mutex> lk(g_arena_mutex);
     size_t held = 0;
     for (const ArenaBlock &b : g_arena) held += b.device == device ? b.bytes : 0;
-    if (held + bytes > ((size_t)48 << 30)) { cudaFree(p); return; }  // park at most 48 GB per device
+    if (held + bytes > ((size_t)120 << 30)) { cudaFree(p); return; }  // park at most 120 GB per device
     g_arena.push_back(ArenaBlock{device, bytes, p});
 }
 
@@ -120,7 +120,7 @@ struct cgrt_ctx {
     // queues
     RayQueue q[2];       // eye pass only: the photon pass keeps its rays in registers
     size_t q_cap[2] = {0, 0};
-    unsigned int *d_qcount = nullptr;  // [0],[1]: eye ray queues; [2..7]: suspended-photon queues of the photon pass
+    unsigned int *d_qcount = nullptr;  // [0],[1]: eye ray queues; [2..7]: suspended-photon queues of the photon pass; [8..13]: work cursors of its 6 trace launches
     // photon pass buffers
     // Deposit tables are double-buffered: the trace kernels of chunk k+1 (stream `tstream`) run while the sort + deposit kernels of
     // chunk k (stream `stream`) drain the other buffer — the latency-bound gather and the fp64-bound tracer share the SMs.
@@ -153,7 +153,12 @@ struct cgrt_ctx {
     int profiling = 0;   // 1: time every photon kernel with events (serialises host and device at the end of each pass)
     double ms[12] = {0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0};
     cudaEvent_t ev[2] = {nullptr, nullptr};
-    size_t photon_chunk = 16u << 20;  // photons per trace launch: bounds the deposit table (chunk * max_depth * 100 B)
+    // photons per trace launch: bounds the deposit table (chunk * max_depth * 104 B) and the two photon queues (chunk * 128 B each).
+    // 0 = as many as fit in 60 % of the device's memory, at most 128 Mi: the deposit kernel amortises a cell's candidate list over the
+    // hits of one chunk that fall into it, so at 4096^2 (16x the cells of 1024^2) a 16 Mi chunk left ~2 hits per cell group and the
+    // kernel re-read 88 GB of candidates per chunk
+    size_t photon_chunk = 0;
+    size_t auto_chunk = 0;
     int counting = 0;  // 1: photon trace kernels also count BVH node visits / triangle tests (roofline accounting)
 };
 
@@ -596,12 +601,12 @@ int cgrt_create(int device, cgrt_ctx **out) {
         delete ctx;
         return CGRT_ERR_CUDA;
     }
-    if (dalloc(ctx, &ctx->d_hp_count, 1) || dalloc(ctx, &ctx->d_qcount, 8) || dalloc(ctx, &ctx->d_ctr, 1) || dalloc(ctx, &ctx->d_tc, 1)) {
+    if (dalloc(ctx, &ctx->d_hp_count, 1) || dalloc(ctx, &ctx->d_qcount, 16) || dalloc(ctx, &ctx->d_ctr, 1) || dalloc(ctx, &ctx->d_tc, 1)) {
         delete ctx;
         return CGRT_ERR_CUDA;
     }
     cudaMemsetAsync(ctx->d_hp_count, 0, sizeof(unsigned int), ctx->stream);
-    cudaMemsetAsync(ctx->d_qcount, 0, 8 * sizeof(unsigned int), ctx->stream);
+    cudaMemsetAsync(ctx->d_qcount, 0, 16 * sizeof(unsigned int), ctx->stream);
     cudaMemsetAsync(ctx->d_ctr, 0, sizeof(Counters), ctx->stream);
     cudaMemsetAsync(ctx->d_tc, 0, sizeof(TravCounters), ctx->stream);
     cudaStreamSynchronize(ctx->stream);
@@ -1101,7 +1106,17 @@ int cgrt_photon_pass(cgrt_ctx *ctx, uint64_t first, uint64_t count) {
     if (!ctx->grid_built) FAIL(CGRT_ERR_INVALID, "build the grid first");
     CK(cudaSetDevice(ctx->device));
     const PassParams &P = ctx->P;
-    const size_t chunk = ctx->photon_chunk;
+    size_t chunk = ctx->photon_chunk ? ctx->photon_chunk : ctx->auto_chunk;
+    if (chunk == 0) {  // once per context: cudaMemGetInfo is not free
+        size_t free_b = 0, total_b = 0;
+        CK(cudaMemGetInfo(&free_b, &total_b));
+        const size_t per_photon = (size_t)P.max_depth * (sizeof(DepositRec) + 2 * sizeof(uint32_t)) * (ctx->overlap ? 2 : 1) + 2 * sizeof(PhotonState);
+        chunk = (total_b / 10 * 6) / per_photon;
+        chunk &= ~(((size_t)1 << 20) - 1);
+        if (chunk > ((size_t)128 << 20)) chunk = (size_t)128 << 20;
+        if (chunk < ((size_t)1 << 20)) chunk = (size_t)1 << 20;
+        ctx->auto_chunk = chunk;
+    }
     const size_t first_chunk = count < chunk ? (size_t)count : chunk;
     if (first_chunk == 0) return CGRT_OK;
     CKS(ensure_photon_buffers(ctx, first_chunk, first_chunk * (size_t)P.max_depth));
@@ -1134,15 +1149,15 @@ int cgrt_photon_pass(cgrt_ctx *ctx, uint64_t first, uint64_t count) {
         mark(T);
         CK(cudaMemsetAsync(B.keys, 0xff, slots * sizeof(uint32_t), T));
         CK(cudaMemsetAsync(B.hist, 0, (size_t)CGRT_NBINS * sizeof(uint32_t), T));
-        CK(cudaMemsetAsync(ctx->d_qcount + 2, 0, 6 * sizeof(unsigned int), T));
+        CK(cudaMemsetAsync(ctx->d_qcount + 2, 0, 12 * sizeof(unsigned int), T));
         unsigned int *qc = ctx->d_qcount + 2;
-#define LAUNCH_PT(F, GRID, QIN, NIN, QOUT, NOUT)                                                                                    \
+#define LAUNCH_PT(F, GRID, QIN, NIN, QOUT, NOUT, CURSOR)                                                                            \
     photon_trace_kernel<F><<<GRID, CGRT_PHOTON_BLOCK, 0, T>>>(ctx->S, P, base, (unsigned int)n, QIN, NIN, QOUT, NOUT, B.rec, B.keys, B.hist, \
-                                                             ctx->cull ? ctx->reach : nullptr, ctx->d_ctr)
+                                                             ctx->cull ? ctx->reach : nullptr, ctx->d_ctr, CURSOR)
         {
             unsigned int want = nblk(n, CGRT_PHOTON_BLOCK);
             stamp(-1);
-            LAUNCH_PT(true, (want < ctx->grid_first ? want : ctx->grid_first), nullptr, nullptr, ctx->pq[0], qc);
+            LAUNCH_PT(true, (want < ctx->grid_first ? want : ctx->grid_first), nullptr, nullptr, ctx->pq[0], qc, qc + 6);
             stamp(9);
         }
         ctx->launches++;
@@ -1161,7 +1176,7 @@ int cgrt_photon_pass(cgrt_ctx *ctx, uint64_t first, uint64_t count) {
                     ctx->launches++;
                 }
                 stamp(7);
-                LAUNCH_PT(false, ctx->grid_cont, qin, nin, qout, qc + pass);
+                LAUNCH_PT(false, ctx->grid_cont, qin, nin, qout, qc + pass, qc + 6 + pass);
                 stamp(8);
                 ctx->launches++;
             }
@@ -1434,6 +1449,7 @@ int cgrt_set_overlap(cgrt_ctx *ctx, int on) {
     CK(cudaStreamSynchronize(ctx->tstream));
     CK(cudaStreamSynchronize(ctx->stream));
     ctx->overlap = on != 0;
+    ctx->auto_chunk = 0;  // two deposit tables: the chunk is sized again
     return CGRT_OK;
 }
 

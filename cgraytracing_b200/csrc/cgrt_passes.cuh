@@ -87,6 +87,9 @@ struct Counters {
 #ifndef CGRT_PHOTON_BLOCK
 #define CGRT_PHOTON_BLOCK 128   /* threads per block of photon_trace_kernel */
 #endif
+#ifndef CGRT_FETCH
+#define CGRT_FETCH 1024        /* indices a warp of photon_trace_kernel draws from the global cursor at a time */
+#endif
 // minimum resident blocks per SM asked of ptxas for the photon kernels (register caps; tuned with A/B builds)
 #ifndef CGRT_TRACE_MINB
 #define CGRT_TRACE_MINB 1   /* 6 (80 registers) and 8 (64 registers, spills) were measured: no gain / slower */
@@ -426,10 +429,19 @@ __global__ void __launch_bounds__(CGRT_PHOTON_BLOCK, CGRT_TRACE_MINB) photon_tra
                                                                         uint64_t first_index, unsigned int n, const PhotonState *__restrict__ qin,
                                                                         const unsigned int *__restrict__ n_in, PhotonState *__restrict__ qout,
                                                                         unsigned int *n_out, DepositRec *__restrict__ rec, uint32_t *__restrict__ keys,
-                                                                        uint32_t *__restrict__ hist, const uint32_t *__restrict__ reach, Counters *ctr) {
+                                                                        uint32_t *__restrict__ hist, const uint32_t *__restrict__ reach, Counters *ctr,
+                                                                        unsigned int *cursor) {
     const unsigned int total = FIRST ? n : *n_in;
-    const unsigned int stride = gridDim.x * CGRT_PHOTON_BLOCK;
-    unsigned int next = blockIdx.x * CGRT_PHOTON_BLOCK + threadIdx.x;
+    // Work is handed out from the head of the index range: a warp draws CGRT_FETCH consecutive indices at a time from a global cursor
+    // (one atomic per CGRT_FETCH photons) and its lanes take them in order. With a static stride per thread the lanes of the grid drift
+    // apart (a photon lives 1 to 5 segments) and after ~1000 photons per thread their deposit records, 96-byte scattered stores, are
+    // spread over gigabytes of the table: the emission kernel went from 5.6 to 8.0 ms per 16 Mi photons between 16 Mi and 64 Mi chunks.
+    const unsigned int lane_id = threadIdx.x & 31u, lt_mask = (1u << lane_id) - 1u;
+    unsigned int wnext = 0, wend = 0;
+    bool exhausted = false;
+    // at most CGRT_FETCH, and small enough that every warp of the grid gets about four turns (the late passes of a round have short queues)
+    unsigned int fetch = total / (((gridDim.x * CGRT_PHOTON_BLOCK) >> 5) * 4u);
+    fetch = fetch > (unsigned int)CGRT_FETCH ? (unsigned int)CGRT_FETCH : (fetch < 32u ? 32u : (fetch & ~31u));
     unsigned int nseg = 0, nhit = 0;
     int mode = PH_NEED;
     d3 o = mk(0, 0, 0), d = mk(0, 0, 1), flux = mk(0, 0, 0), n_ff = mk(0, 0, 1);
@@ -443,24 +455,44 @@ __global__ void __launch_bounds__(CGRT_PHOTON_BLOCK, CGRT_TRACE_MINB) photon_tra
         // reconvergence point, lanes that finish a segment early run ahead and the warp falls apart into sub-warps for good.
         __syncwarp();
         // ---- stage 1: a ray for every lane
-        if (mode == PH_NEED && !done) {
-            if (next >= total) {
-                done = true;
-            } else if (FIRST) {
-                local = next; depth = 0;
-                mode = PH_FRESH;
-                next += stride;
-            } else {
-                const double2 *q = reinterpret_cast<const double2 *>(qin + next);
-                double2 q0 = __ldg(q), q1 = __ldg(q + 1), q2 = __ldg(q + 2), q3 = __ldg(q + 3), q4 = __ldg(q + 4), q5 = __ldg(q + 5), q6 = __ldg(q + 6);
-                o = mk(q0.x, q0.y, q1.x); d = mk(q1.y, q2.x, q2.y); flux = mk(q3.x, q3.y, q4.x);
-                A.nearest = q4.y; A.nrm = mk(q5.x, q5.y, q6.x);
-                long long ip = __double_as_longlong(q6.y);
-                A.id = (int)(uint32_t)ip; A.prim = (int)(uint32_t)(ip >> 32);
-                uint64_t meta = (uint64_t)__double_as_longlong(__ldg(reinterpret_cast<const double *>(q + 7)));
-                local = (uint32_t)meta; depth = (int)(meta >> 32);
-                mode = PH_RESOLVED;  // arrives with the closest hit of its pending segment
-                next += stride;
+        {
+            bool want = mode == PH_NEED && !done;
+            unsigned int need = __ballot_sync(0xffffffffu, want);
+            while (need) {  // warp-uniform
+                if (wnext >= wend) {
+                    if (!exhausted) {
+                        unsigned int base = 0;
+                        if (lane_id == 0) base = atomicAdd(cursor, fetch);
+                        base = __shfl_sync(0xffffffffu, base, 0);
+                        if (base >= total) { exhausted = true; }
+                        else { wnext = base; wend = (total - base > fetch) ? base + fetch : total; }
+                    }
+                    if (exhausted) {
+                        if (want) done = true;
+                        break;
+                    }
+                }
+                const unsigned int avail = wend - wnext, rank = __popc(need & lt_mask), cnt = __popc(need);
+                if (want && rank < avail) {
+                    const unsigned int next = wnext + rank;
+                    want = false;
+                    if (FIRST) {
+                        local = next; depth = 0;
+                        mode = PH_FRESH;
+                    } else {
+                        const double2 *q = reinterpret_cast<const double2 *>(qin + next);
+                        double2 q0 = __ldg(q), q1 = __ldg(q + 1), q2 = __ldg(q + 2), q3 = __ldg(q + 3), q4 = __ldg(q + 4), q5 = __ldg(q + 5), q6 = __ldg(q + 6);
+                        o = mk(q0.x, q0.y, q1.x); d = mk(q1.y, q2.x, q2.y); flux = mk(q3.x, q3.y, q4.x);
+                        A.nearest = q4.y; A.nrm = mk(q5.x, q5.y, q6.x);
+                        long long ip = __double_as_longlong(q6.y);
+                        A.id = (int)(uint32_t)ip; A.prim = (int)(uint32_t)(ip >> 32);
+                        uint64_t meta = (uint64_t)__double_as_longlong(__ldg(reinterpret_cast<const double *>(q + 7)));
+                        local = (uint32_t)meta; depth = (int)(meta >> 32);
+                        mode = PH_RESOLVED;  // arrives with the closest hit of its pending segment
+                    }
+                }
+                wnext += cnt < avail ? cnt : avail;
+                need = __ballot_sync(0xffffffffu, want);
             }
         }
         if (__all_sync(0xffffffffu, done)) break;
