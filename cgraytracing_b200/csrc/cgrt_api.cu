@@ -484,7 +484,7 @@ int ensure_photon_buffers(cgrt_ctx *ctx, size_t photons, size_t slots) {
         for (auto &b : ctx->dep) {
             CKS(dalloc(ctx, &b.hist, (size_t)CGRT_NBINS));
             CKS(dalloc(ctx, &b.bsum, (size_t)CGRT_NBINS / (CGRT_SCAN_BLOCK * CGRT_SCAN_ITEMS)));
-            CKS(dalloc(ctx, &b.nvalid, 1));
+            CKS(dalloc(ctx, &b.nvalid, 2));
             CK(cudaEventCreateWithFlags(&b.traced, cudaEventDisableTiming));
             CK(cudaEventCreateWithFlags(&b.drained, cudaEventDisableTiming));
         }

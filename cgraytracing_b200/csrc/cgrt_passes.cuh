@@ -754,7 +754,7 @@ __device__ __forceinline__ void deposit_pair(const HitShared<ACC> &H, uint32_t h
 
 template <int ACC>
 __global__ void __launch_bounds__(CGRT_DEPOSIT_BLOCK) photon_deposit_kernel(const __grid_constant__ PassParams P, const DepositRec *__restrict__ rec,
-                                                                            const uint32_t *__restrict__ perm, const uint32_t *__restrict__ n_valid,
+                                                                            const uint32_t *__restrict__ perm, uint32_t *__restrict__ n_valid,
                                                                             const uint32_t *__restrict__ cell_start,
                                                                             const float4 *__restrict__ pre, const float4 *__restrict__ pre_n,
                                                                             const float4 *__restrict__ pre_f, const HpHot *__restrict__ hot,
@@ -777,8 +777,6 @@ __global__ void __launch_bounds__(CGRT_DEPOSIT_BLOCK) photon_deposit_kernel(cons
     uint32_t *cidx = cidx_all[wib];
     uint32_t *queue = queue_all[wib];
     const unsigned int lt = (1u << lane) - 1u;
-    const size_t warp = ((size_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
-    const size_t nwarps = ((size_t)gridDim.x * blockDim.x) >> 5;
     unsigned long long cand_total = 0;
     unsigned int ndep = 0, npair = 0;
     const int idx = lane / 9, idy = (lane / 3) % 3, idz = lane % 3;  // idx outermost, idz innermost (main.cpp:110-112)
@@ -793,7 +791,14 @@ __global__ void __launch_bounds__(CGRT_DEPOSIT_BLOCK) photon_deposit_kernel(cons
             deposit_pair<ACC>(H, hl, cidx[b], cpre[b], cnrm[b], ACC == 1 ? cf[b] : make_float4(0.f, 0.f, 0.f, 0.f), rec, hot, hp_f, acc, ndep);
         }
     };
-    for (size_t span = warp * CGRT_DEPOSIT_SPAN; span < n_slots; span += nwarps * CGRT_DEPOSIT_SPAN) {
+    // spans are handed out from a global cursor (n_valid[1], zeroed by bin_scan_sums_kernel); the next one is requested before the
+    // current one is processed, so the atomic's round trip is never waited for
+    uint32_t span32 = 0;
+    if (lane == 0) span32 = atomicAdd(n_valid + 1, (uint32_t)CGRT_DEPOSIT_SPAN);
+    span32 = __shfl_sync(0xffffffffu, span32, 0);
+    for (size_t span = span32; span < n_slots;) {
+        uint32_t next32 = 0;
+        if (lane == 0) next32 = atomicAdd(n_valid + 1, (uint32_t)CGRT_DEPOSIT_SPAN);
         const size_t span_end = span + CGRT_DEPOSIT_SPAN < n_slots ? span + CGRT_DEPOSIT_SPAN : n_slots;
         for (size_t base = span; base < span_end; base += 32) {
             // ---- lane = one deposit record of the batch
@@ -936,6 +941,7 @@ __global__ void __launch_bounds__(CGRT_DEPOSIT_BLOCK) photon_deposit_kernel(cons
                 }
             }
         }
+        span = (size_t)__shfl_sync(0xffffffffu, next32, 0);
     }
     // counters: warp-reduce then one atomic per warp
     unsigned long long dep_total = ndep;
@@ -998,7 +1004,7 @@ __global__ void __launch_bounds__(CGRT_SCAN_BLOCK) bin_scan_sums_kernel(uint32_t
     uint32_t total;
     uint32_t ex = block_exclusive_scan_1024(v, ws, total);
     if ((int)threadIdx.x < nblocks) block_sums[threadIdx.x] = ex;
-    if (threadIdx.x == 0) *n_valid = total;
+    if (threadIdx.x == 0) { n_valid[0] = total; n_valid[1] = 0u; }  // [1]: the span cursor of photon_deposit_kernel
 }
 // phase 3 fused into the scatter: cursor of bin b = hist[b] + block_sums[b / 4096]
 __global__ void __launch_bounds__(256) bin_scatter_kernel(const uint32_t *__restrict__ keys, size_t n_slots, uint32_t *__restrict__ hist,
