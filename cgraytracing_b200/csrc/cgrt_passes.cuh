@@ -88,7 +88,7 @@ struct Counters {
 #define CGRT_PHOTON_BLOCK 128   /* threads per block of photon_trace_kernel */
 #endif
 #ifndef CGRT_FETCH
-#define CGRT_FETCH 1024        /* indices a warp of photon_trace_kernel draws from the global cursor at a time */
+#define CGRT_FETCH 256         /* indices a warp of photon_trace_kernel draws from the global cursor at a time (64-256: 4.95 ms, 1024: 5.07 ms) */
 #endif
 // minimum resident blocks per SM asked of ptxas for the photon kernels (register caps; tuned with A/B builds)
 #ifndef CGRT_TRACE_MINB
@@ -640,7 +640,9 @@ __global__ void __launch_bounds__(CGRT_PHOTON_BLOCK, CGRT_TRACE_MINB) photon_tra
 // (SURVEY Q13). ACC: 0 = fp64 atomics {dflux.xyz, m}; 1 = one red.global.add.v4.f32.
 // ---------------------------------------------------------------------------------------------------------------------
 #define CGRT_DEPOSIT_BLOCK 256
-#define CGRT_DEPOSIT_SPAN 128   /* sorted records per warp */
+#ifndef CGRT_DEPOSIT_SPAN
+#define CGRT_DEPOSIT_SPAN 256   /* sorted records a warp takes from the cursor at a time. Measured 64 / 128 / 256 / 512 / 1024 / 2048 / 4096: 9.2 / 7.25 / 6.45 / 6.45 / 6.6 / 6.95 / 7.2 ms: consecutive batches of a warp hit the same candidate lists in L1, long spans balance worse */
+#endif
 
 __device__ __forceinline__ double4 ldg4(const double4 *p) {  // 32 bytes of a deposit record: streamed (evict-first), two 16-byte loads
     const double2 *q = reinterpret_cast<const double2 *>(p);
