@@ -565,23 +565,13 @@ __global__ void __launch_bounds__(CGRT_PHOTON_BLOCK, CGRT_TRACE_MINB) photon_tra
                 const bool reachable = (rword >> (rh & 31u)) & 1u;
                 if (reachable) {
                     double2 *r = reinterpret_cast<double2 *>(rec + slot);  // streamed: written once, read once by the deposit kernel
-#ifndef CGRT_EXP_NOREC
                     __stcs(r, make_double2(X.x, X.y)); __stcs(r + 1, make_double2(X.z, n_ff.x));
                     __stcs(r + 2, make_double2(n_ff.y, n_ff.z)); __stcs(r + 3, make_double2(flux.x, flux.y));
                     __stcs(r + 4, make_double2(flux.z, __longlong_as_double(((long long)(uint32_t)iy << 32) | (uint32_t)ix)));
                     __stcs(r + 5, make_double2(__longlong_as_double((long long)(uint32_t)iz), 0.0));
-#else
-                    if (X.x == 1e300) __stcs(r, make_double2(X.x, X.y));
-#endif
                     const uint32_t bin = cell_bin(ix, iy, iz);
-#ifndef CGRT_EXP_NOKEY
                     keys[slot] = bin;
-#endif
-#ifndef CGRT_EXP_NOHIST
                     atomicAdd(hist + bin, 1u);  // histogram of the counting sort, fused into the producer
-#else
-                    if (X.x == 1e300) atomicAdd(hist + bin, 1u);
-#endif
                 }
             }
             if (depth + 1 >= P.max_depth) {
