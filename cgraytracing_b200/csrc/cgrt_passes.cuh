@@ -886,25 +886,32 @@ __global__ void __launch_bounds__(CGRT_DEPOSIT_BLOCK) photon_deposit_kernel(cons
                         }
                         nc += __popc(km);
                     }
+                    // pad the staged list to a multiple of 8 with records no hit can pass, so that the scan runs in unguarded blocks of 8
+                    if (lane < 8 && nc + lane < ((nc + 7) & ~7)) cpre[nc + lane] = make_float4(0.f, 0.f, 0.f, -1.f);
                     __syncwarp();
                     // ---- prefilter: every lane tests its own hit against the staged candidates (shared-memory broadcast)
                     unsigned int m_lo = 0, m_hi = 0;
-#pragma unroll 8
-                    for (int k = 0; k < 32; k++) {
-                        if (k < nc) {
-                            const float4 q = cpre[k];
-                            const float ddx = q.x - hx, ddy = q.y - hy, ddz = q.z - hz;
-                            m_lo |= (fmaf(ddz, ddz, fmaf(ddy, ddy, ddx * ddx)) <= q.w) ? (1u << k) : 0u;
-                        }
-                    }
-                    if (nc > 32) {
-#pragma unroll 8
-                        for (int k = 0; k < 32; k++) {
-                            if (k + 32 < nc) {
-                                const float4 q = cpre[32 + k];
+                    {
+                        const int n_lo = nc < 32 ? nc : 32;
+                        for (int k0 = 0; k0 < n_lo; k0 += 8) {
+                            unsigned int bits = 0;
+#pragma unroll
+                            for (int j = 0; j < 8; j++) {
+                                const float4 q = cpre[k0 + j];
                                 const float ddx = q.x - hx, ddy = q.y - hy, ddz = q.z - hz;
-                                m_hi |= (fmaf(ddz, ddz, fmaf(ddy, ddy, ddx * ddx)) <= q.w) ? (1u << k) : 0u;
+                                bits |= (fmaf(ddz, ddz, fmaf(ddy, ddy, ddx * ddx)) <= q.w) ? (1u << j) : 0u;
                             }
+                            m_lo |= bits << k0;
+                        }
+                        for (int k0 = 32; k0 < nc; k0 += 8) {
+                            unsigned int bits = 0;
+#pragma unroll
+                            for (int j = 0; j < 8; j++) {
+                                const float4 q = cpre[k0 + j];
+                                const float ddx = q.x - hx, ddy = q.y - hy, ddz = q.z - hz;
+                                bits |= (fmaf(ddz, ddz, fmaf(ddy, ddy, ddx * ddx)) <= q.w) ? (1u << j) : 0u;
+                            }
+                            m_hi |= bits << (k0 - 32);
                         }
                     }
                     if (!((grp >> lane) & 1u)) { m_lo = 0; m_hi = 0; }
