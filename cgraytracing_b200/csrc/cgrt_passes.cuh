@@ -630,6 +630,9 @@ __global__ void __launch_bounds__(CGRT_PHOTON_BLOCK, CGRT_TRACE_MINB) photon_tra
 // (SURVEY Q13). ACC: 0 = fp64 atomics {dflux.xyz, m}; 1 = one red.global.add.v4.f32.
 // ---------------------------------------------------------------------------------------------------------------------
 #define CGRT_DEPOSIT_BLOCK 256
+#ifndef CGRT_DEPOSIT_MINB
+#define CGRT_DEPOSIT_MINB 4   /* resident blocks per SM asked of ptxas (64 registers; 5 = 48 registers was measured: 6.54 vs 6.45 ms) */
+#endif
 #ifndef CGRT_DEPOSIT_SPAN
 #define CGRT_DEPOSIT_SPAN 256   /* sorted records a warp takes from the cursor at a time. Measured 64 / 128 / 256 / 512 / 1024 / 2048 / 4096: 9.2 / 7.25 / 6.45 / 6.45 / 6.6 / 6.95 / 7.2 ms: consecutive batches of a warp hit the same candidate lists in L1, long spans balance worse */
 #endif
@@ -745,7 +748,7 @@ __device__ __forceinline__ void deposit_pair(const HitShared<ACC> &H, uint32_t h
 }
 
 template <int ACC>
-__global__ void __launch_bounds__(CGRT_DEPOSIT_BLOCK) photon_deposit_kernel(const __grid_constant__ PassParams P, const DepositRec *__restrict__ rec,
+__global__ void __launch_bounds__(CGRT_DEPOSIT_BLOCK, CGRT_DEPOSIT_MINB) photon_deposit_kernel(const __grid_constant__ PassParams P, const DepositRec *__restrict__ rec,
                                                                             const uint32_t *__restrict__ perm, uint32_t *__restrict__ n_valid,
                                                                             const uint32_t *__restrict__ cell_start,
                                                                             const float4 *__restrict__ pre, const float4 *__restrict__ pre_n,
