@@ -580,6 +580,7 @@ int cgrt_create(int device, cgrt_ctx **out) {
         if (const char *e = getenv("CGRT_PHOTON_CHUNK")) { long long c = atoll(e); if (c > 0) ctx->photon_chunk = (size_t)c; }  // tests: force multi-chunk passes
         // resident blocks per SM of the two pipelined halves (dev knobs: how the trace and the deposit stream share an SM)
         if (const char *e = getenv("CGRT_TRACE_BPS")) { unsigned int b = (unsigned int)atoi(e) * (unsigned int)sms; if (b) { ctx->grid_first = b; ctx->grid_cont = b; ctx->trav_grid = b; } }
+        if (const char *e = getenv("CGRT_TRAV_BPS")) { unsigned int b = (unsigned int)atoi(e) * (unsigned int)sms; if (b) ctx->trav_grid = b; }
         if (const char *e = getenv("CGRT_DEPOSIT_BPS")) { unsigned int b = (unsigned int)atoi(e) * (unsigned int)sms; if (b) ctx->deposit_grid = b; }
         cudaGetLastError();
     }
