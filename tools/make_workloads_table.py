@@ -6,9 +6,9 @@ names = {"c1_spheres_bezier": "c1 512², spheres + Bezier vase, 1 Mi photons/rou
          "c3_dragon_glass": "c3 1024², glass dragon, 16 Mi (headline)", "c4_bump_dof": "c4 1920×1080, bump floor + DOF ×4 samples, 16 Mi",
          "c5_dragon_4096": "c5 4096², dragon, 128 Mi per step on 1 GPU"}
 out = ["# r01 — every BASELINE config on one B200, and the multi-GPU points\n",
-       "`python bench.py --workload <name>` (short runs: `--steps 3 --warmup 2 --e2e-rounds 2`; c3 is the full default run of `r01_final_bench.json`). "
+       "`python bench.py --workload <name>` (`--steps 3 --warmup 3`; c3 is the full default run of `r01_final_bench.json`; c5 `--photons 134217728 --steps 2 --warmup 1`). "
        "Full lines: `profiles/r01_final_bench_<name>.json`. `photons/s` is device-timed over whole rounds (trace + sort + deposit + update); `e2e` is a whole "
-       "`render()` from host arrays to the host image through the C ABI (c3: 50 rounds; the others 2 rounds, so their setup weighs more); `CPU` is the oracle on "
+       "`render()` of the config's own round count (10 / 20 / 50 / 20) from host arrays to the host image through the C ABI; `CPU` is the oracle on "
        "the box's 16 host threads; `alg. frac` is `roofline.frac` of the deposit kernel (algorithmic bytes of SURVEY 8(d) / time / 6,552 GB/s: above 1 because "
        "candidates are staged once per cell group in shared memory instead of being read once per photon hit).\n",
        "| config | hitpoints | photons/s | ms/step | trace / sort / deposit / update (ms) | eye rays/s | alg. frac | e2e photons/s | CPU photons/s |", "|---|---|---|---|---|---|---|---|---|"]
