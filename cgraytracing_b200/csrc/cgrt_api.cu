@@ -1172,8 +1172,16 @@ int cgrt_photon_pass(cgrt_ctx *ctx, uint64_t first, uint64_t count) {
                     ctx->launches++;
                 }
                 if (ctx->S.nbvh > 0) {
-                    if (ctx->counting) photon_traverse_kernel<true><<<resume_grid, 128, 0, T>>>(ctx->S, qin, nin, ctx->d_tc);
-                    else photon_traverse_kernel<false><<<resume_grid, 128, 0, T>>>(ctx->S, qin, nin, ctx->d_tc);
+                    // every tree within CGRT_F32_BOUND (all BASELINE scenes): the instantiation without fp64 box arithmetic
+                    bool f32 = getenv("CGRT_TRAV_EXACT") == nullptr;
+                    for (int b = 0; b < ctx->S.nbvh; b++) f32 = f32 && ctx->S.bvh[b].f32_ok;
+                    if (ctx->counting) {
+                        if (f32) photon_traverse_kernel<true, true><<<resume_grid, 128, 0, T>>>(ctx->S, qin, nin, ctx->d_tc);
+                        else photon_traverse_kernel<true, false><<<resume_grid, 128, 0, T>>>(ctx->S, qin, nin, ctx->d_tc);
+                    } else {
+                        if (f32) photon_traverse_kernel<false, true><<<resume_grid, 128, 0, T>>>(ctx->S, qin, nin, ctx->d_tc);
+                        else photon_traverse_kernel<false, false><<<resume_grid, 128, 0, T>>>(ctx->S, qin, nin, ctx->d_tc);
+                    }
                     ctx->launches++;
                 }
                 stamp(7);

@@ -385,6 +385,84 @@ __device__ __forceinline__ bool bvh_closest(const BvhDev &B, d3 o, d3 d, double 
     return best_leaf >= 0;
 }
 
+// The same traversal for trees that lie within CGRT_F32_BOUND (every mesh of the BASELINE scenes), without any fp64 box arithmetic:
+// a ray that starts farther out than the bound is re-based for the box tests only — its entry distance t0 into the padded root box is
+// taken in fp64 once, the float slab tests then run from o + d t0 (which lies on the root box, inside the bound) against best - t0.
+// The triangle test keeps the original origin and the reference's fp64 arithmetic. Without the fp64 slab path the kernel keeps six
+// doubles less alive per thread (photon_traverse_kernel is capped at 64 registers).
+template <bool COUNT>
+__device__ __forceinline__ bool bvh_closest_f32(const BvhDev &B, d3 o, d3 d, double tmax, double &t_out, int &leaf_out, TravCounters *tc) {
+    double t0 = 0.0;
+    d3 ob = o;
+    if (!(fabs(o.x) <= CGRT_F32_BOUND && fabs(o.y) <= CGRT_F32_BOUND && fabs(o.z) <= CGRT_F32_BOUND)) {
+        const double ix = 1.0 / d.x, iy = 1.0 / d.y, iz = 1.0 / d.z;
+        const double tx0 = ((double)B.root_lo[0] - o.x) * ix, tx1 = ((double)B.root_hi[0] - o.x) * ix;
+        const double ty0 = ((double)B.root_lo[1] - o.y) * iy, ty1 = ((double)B.root_hi[1] - o.y) * iy;
+        const double tz0 = ((double)B.root_lo[2] - o.z) * iz, tz1 = ((double)B.root_hi[2] - o.z) * iz;
+        const double tn = fmax(fmax(fmin(tx0, tx1), fmin(ty0, ty1)), fmax(fmin(tz0, tz1), 0.0));
+        const double tf = fmin(fmin(fmax(tx0, tx1), fmax(ty0, ty1)), fmin(fmax(tz0, tz1), tmax));
+        if (!(tn <= tf)) { t_out = tmax; leaf_out = -1; return false; }  // misses the root box
+        t0 = tn * (1.0 - 1e-12);  // never beyond the true entry
+        ob = o + d * t0;
+    }
+    const float ox = (float)ob.x, oy = (float)ob.y, oz = (float)ob.z;
+    const float ix = 1.0f / (float)d.x, iy = 1.0f / (float)d.y, iz = 1.0f / (float)d.z;
+    double best = tmax;
+    float best_up = __double2float_ru(tmax - t0);
+    int best_leaf = -1;
+    int stack[64];
+    int sp = 0;
+    int node = B.root_is_leaf ? ~0 : 0;
+    for (;;) {
+        if (node >= 0) {
+            const float4 *q = reinterpret_cast<const float4 *>(B.nodes + node);
+            float4 q0 = __ldg(q), q1 = __ldg(q + 1), q2 = __ldg(q + 2), q3 = __ldg(q + 3);
+            if (COUNT) tc->node_visits++;
+            int c0 = __float_as_int(q3.x), c1 = __float_as_int(q3.y);
+            float tn0, tn1;
+            bool h0, h1;
+            {
+                const float tx0 = (q0.x - ox) * ix, tx1 = (q0.w - ox) * ix, ty0 = (q0.y - oy) * iy, ty1 = (q1.x - oy) * iy;
+                const float tz0 = (q0.z - oz) * iz, tz1 = (q1.y - oz) * iz;
+                tn0 = fmaxf(fmaxf(fminf(tx0, tx1), fminf(ty0, ty1)), fmaxf(fminf(tz0, tz1), 0.0f));
+                h0 = tn0 <= fminf(fminf(fmaxf(tx0, tx1), fmaxf(ty0, ty1)), fminf(fmaxf(tz0, tz1), best_up));
+            }
+            {
+                const float tx0 = (q1.z - ox) * ix, tx1 = (q2.y - ox) * ix, ty0 = (q1.w - oy) * iy, ty1 = (q2.z - oy) * iy;
+                const float tz0 = (q2.x - oz) * iz, tz1 = (q2.w - oz) * iz;
+                tn1 = fmaxf(fmaxf(fminf(tx0, tx1), fminf(ty0, ty1)), fmaxf(fminf(tz0, tz1), 0.0f));
+                h1 = tn1 <= fminf(fminf(fmaxf(tx0, tx1), fmaxf(ty0, ty1)), fminf(fmaxf(tz0, tz1), best_up));
+            }
+            if (h0 && h1) {
+                if (tn1 < tn0) { int tmp = c0; c0 = c1; c1 = tmp; }
+                stack[sp++] = c1;
+                node = c0;
+            } else if (h0) {
+                node = c0;
+            } else if (h1) {
+                node = c1;
+            } else {
+                if (sp == 0) break;
+                node = stack[--sp];
+            }
+        } else {
+            int leaf = ~node;
+            if (COUNT) tc->tri_tests++;
+            double t;
+            if (tri_intersect(B.tris + leaf, o, d, t) && t < best) {
+                best = t;
+                best_up = __double2float_ru(t - t0);
+                best_leaf = leaf;
+            }
+            if (sp == 0) break;
+            node = stack[--sp];
+        }
+    }
+    t_out = best;
+    leaf_out = best_leaf;
+    return best_leaf >= 0;
+}
+
 // ---------------------------------------------------------------------------------------------------------------
 // Bezier surface of revolution (bezier.h). The reference solves F(t,u,theta)=0 by Newton from 10 random starts;
 // here the same Newton iteration (same F, same Jacobian, same acceptance test) is started from a deterministic
@@ -664,7 +742,7 @@ __device__ __forceinline__ void bvh_merge(const SceneDev &S, int i, int leaf, do
 }
 
 // Resolve deferred object i for one ray and merge it into A with the (len, index) order of main.cpp:55-63.
-template <bool COUNT, bool BEZ>
+template <bool COUNT, bool BEZ, bool F32 = false>
 __device__ __forceinline__ bool deferred_resolve(const SceneDev &S, int i, d3 o, d3 d, double lim, HitAcc &A, TravCounters *tc) {
     const ObjDev &O = S.obj[i];
     if (O.kind == OBJ_BEZIER) {
@@ -678,7 +756,7 @@ __device__ __forceinline__ bool deferred_resolve(const SceneDev &S, int i, d3 o,
         return false;
     }
     double t; int leaf;
-    if (!bvh_closest<COUNT>(S.bvh[O.bvh], o, d, lim, t, leaf, tc)) return false;
+    if (!(F32 ? bvh_closest_f32<COUNT>(S.bvh[O.bvh], o, d, lim, t, leaf, tc) : bvh_closest<COUNT>(S.bvh[O.bvh], o, d, lim, t, leaf, tc))) return false;
     bvh_merge(S, i, leaf, t, A);
     return true;
 }

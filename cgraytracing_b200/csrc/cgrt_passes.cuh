@@ -345,7 +345,7 @@ __device__ __forceinline__ uint32_t cell_bin(int ix, int iy, int iz) {
 // overhead, 224 bytes of spills at 64 registers) and the issue rate dropped from 61 % to 47 %: 6.8-7.0 ms vs 5.7 ms per round.
 // Also rejected: a warp-synchronous traversal that postpones leaves and tests the postponed triangles of 4/8/16 lanes together (the fp64
 // triangle test is 27 % of the instructions at 1.7 live lanes): 6.2-6.3 ms — the two ballots per node step cost more than the test saves.)
-template <bool COUNT>
+template <bool COUNT, bool F32>
 __global__ void __launch_bounds__(128, CGRT_TRAV_MINB) photon_traverse_kernel(const __grid_constant__ SceneDev S, PhotonState *__restrict__ q,
                                                               const unsigned int *__restrict__ n_in, TravCounters *tcg) {
     const unsigned int total = *n_in;
@@ -362,7 +362,7 @@ __global__ void __launch_bounds__(128, CGRT_TRAV_MINB) photon_traverse_kernel(co
             if (S.obj[k].bvh < 0) continue;  // Bezier objects were resolved by photon_bezier_kernel
             double lim;
             if (!deferred_wanted(S, k, o, d, A, lim)) continue;
-            changed |= deferred_resolve<COUNT, false>(S, k, o, d, lim, A, &tcl);
+            changed |= deferred_resolve<COUNT, false, F32>(S, k, o, d, lim, A, &tcl);
         }
         if (changed) {
             q[i].nearest = A.nearest;
