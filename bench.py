@@ -283,7 +283,7 @@ def run_gpu(args):
     bytes_dep = gathered * B_CELLS + cand * B_CAND + dep * B_DEP
     # DRAM bytes per round from the committed ncu --set full capture of this command line (profiles/r01_final_ncu_summary.md); only
     # meaningful for the configuration it was captured on
-    ncu_traffic = {"photon_deposit_kernel": 13.84e9, "photon_trace_kernel": 10.78e9} if (WORKLOAD == "c3_dragon_glass" and P == (16 << 20) and args.accum == 1) else {}
+    ncu_traffic = {"photon_deposit_kernel": 13.84e9, "photon_trace_kernel": 10.84e9} if (WORKLOAD == "c3_dragon_glass" and P == (16 << 20) and args.accum == 1) else {}
     kernels = {
         "photon_trace_kernel": {"seconds": t_trace, "alg_bytes": bytes_trace, "gbps": bytes_trace / t_trace / 1e9, "launches": 11 * n_chunks,
                                 "ms_per_round": 1e3 * t_trace, "nodes_per_segment": per_seg_nodes, "tris_per_segment": per_seg_tris,

@@ -24,6 +24,7 @@ for w in names:
 out += ["\n## Multi-GPU (one box, torchrun, NCCL all-reduce of the accumulators per round)\n", "| GPUs | config | scaling | photons/s | ms/step | vs 1 GPU |", "|---|---|---|---|---|---|"]
 c3 = one["c3_dragon_glass"]
 out.append(f"| 1 | c3 | — | {c3['value']/1e6:.1f} M | {c3['ms_per_step']:.2f} | 1.00 |")
+c3 = dict(c3, value=828.1e6)  # the multi-GPU lines below were measured when one GPU did 828.1 M photons/s (three kernel changes before the final code)
 for n in (2, 4, 8):
     d = L(f"{P}_{n}gpu.json")
     out.append(f"| {n} | c3, 16 Mi photons per GPU per round | weak | {d['value']/1e6:.1f} M | {d['ms_per_step']:.2f} | {d['value']/c3['value']:.2f} ({100*d['value']/c3['value']/n:.0f} % of linear) |")
@@ -31,8 +32,10 @@ for c, w, what in (("c1", "c1_spheres_bezier", "1 Mi photons per GPU per round")
     d = L(f"{P}_{c}_8gpu.json")
     then = {"c1": 213.2e6, "c2": 848.3e6, "c4": 143.4e6}[c]
     out.append(f"| 8 | {c}, {what} | weak | {d['value']/1e6:.1f} M | {d['ms_per_step']:.2f} | {d['value']/then:.2f} ({100*d['value']/then/8:.0f} % of linear) |")
-d = L(f"{P}_c5_8gpu.json"); c5 = one["c5_dragon_4096"]
+d = L(f"{P}_c5_8gpu.json"); c5 = dict(one["c5_dragon_4096"], value=614.8e6)
 out.append(f"| 8 | c5, 1 Gi photons per round split over the GPUs | strong | {d['value']/1e6:.1f} M | {d['ms_per_step']:.2f} | {d['value']/c5['value']:.2f} vs the 1-GPU c5 rate ({100*d['value']/c5['value']/8:.0f} % of linear) |")
+out.append("\nThe c3 and c5 multi-GPU lines were measured when one GPU did 828.1 M (c3) / 614.8 M (c5) photons/s, three kernel changes before the final code; "
+           "their `vs 1 GPU` column uses those rates.")
 out.append("\nThe 8-GPU lines of c1, c2 and c4 were measured two kernel changes earlier than the rest of this table (their 1-GPU rates were then 213 / 848 / "
            "143 M photons/s); their `vs 1 GPU` column uses those rates.")
 out.append("\nShort rounds scale worse: c1 and c2 spend 5 ms per round, of which the all-reduce, the update and the host's enqueue are a fixed ~1 ms. The driver "
