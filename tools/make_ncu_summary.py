@@ -33,16 +33,17 @@ for name in ("photon_deposit", "photon_traverse", "photon_trace"):
     out.append(f"### {name}\n```\n{src}```\n")
 out.append("""## 5. Reading
 
-* No kernel is bound by HBM (DRAM throughput <= 32 % of the measured copy peak) or by launch overhead (16 launches per ~22 ms round).
-* photon_trace_kernel (emission and continuation) is bound by dependent fp64 latency: 4 warps per scheduler (108 registers), 0.47 issue
+* No kernel is bound by HBM (DRAM throughput <= 35 % of the measured copy peak) or by launch overhead (16 launches per ~20 ms round).
+* photon_trace_kernel (emission and continuation) is bound by dependent fp64 latency: 4 warps per scheduler (114 registers), ~0.48 issue
   slots per cycle, warp states `wait` + `short_scoreboard` + `long_scoreboard` ~ 65 %. Measured and found flat: block size 64/96/128,
-  register caps of 96/80/64, three plane quotients in flight (kept, -5 %).
+  register caps of 96/80/64. Kept: three plane quotients in flight, work drawn from the head of the index range, float root-box test.
 * photon_traverse_kernel is bound by divergence: 6-9 of 32 lanes live per instruction (one ray per lane, path lengths from 1 to hundreds
-  of nodes; the fp64 triangle test runs at 1.7 lanes). Three restructurings that raise the live-lane count (while-while, per-lane refill,
-  postponed leaf batches) were measured slower: the kernel's issue rate falls faster than its instruction count.
-* photon_deposit_kernel is close to issue-bound (0.66 issue slots per cycle, 29.7 of 32 lanes live, l1tex 80 %): the prefilter scan is
-  27 % of its instructions, the drain into the pair queue 23 %; the fp64 exact test left the profile when pairs started being decided
-  in fp32 from shared memory (line `deposit_pair`).
+  of nodes; the fp64 triangle test runs at 1.7 lanes). Restructurings that raise the live-lane count (while-while, per-lane refill,
+  postponed leaf batches) and a float triangle pretest were measured slower; dropping all fp64 box arithmetic was kept (-9 %).
+* photon_deposit_kernel is bound by the L1 / shared-memory pipe (l1tex ~ 90 %, ~0.59 issue slots per cycle, 28 of 32 lanes live): the
+  prefilter scan over the staged candidates and the drain into the pair queue are shared-memory traffic; the fp64 exact test left the
+  profile when pairs started being decided in fp32 from shared memory (`deposit_pair`).
 """)
+
 open(f"profiles/{tag}_ncu_summary.md", "w").write("\n".join(out))
 print("wrote", f"profiles/{tag}_ncu_summary.md")
