@@ -447,3 +447,24 @@ def test_no_out_of_bounds_writes_with_fenced_buffers():
     r = subprocess.run([sys.executable, os.path.join(root, "tools", "sanitize_probe.py")], env=env, capture_output=True, text=True, timeout=900)
     assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-2000:]
     assert "guard mode 1 damaged fence bytes 0" in r.stdout
+
+
+@pytest.mark.parametrize("hashsize", [97, 4099])
+def test_colliding_buckets_are_listed_like_the_reference(gpu, oracle_lib, hashsize):
+    """A tiny hash table: many cells share a bucket and several of a photon's 27 neighbour cells hash to the same one, which the reference
+    then scans (and deposits into) once per listing (hash.h:35-42, main.cpp:105-122). Counts and fluxes must still equal the
+    oracle's, and the GPU must scan exactly the reference's candidates when the reach-map culling is off."""
+    W, H, NPH = 64, 48, 12000
+    s, cfg, g, o = make(gpu, oracle_lib, "c1_spheres", dict(width=W, height=H, into_rule=1, update_mode=1, hashsize=hashsize), None)
+    with g:
+        g.set_culling(False)
+        g.eye_pass(); g.build_grid()
+        o.eye_pass()
+        g.photon_pass(0, NPH); o.photon_pass(0, NPH)
+        df, m = g.download_accum()
+        odf, om = o.download_accum()
+        assert np.array_equal(m.astype(np.int64), om.astype(np.int64))
+        assert np.allclose(df, odf, rtol=1e-9, atol=1e-12)
+        gc, oc = g.counters(), o.counters()
+        assert gc["deposits"] == oc["deposits"] and gc["candidates"] == oc["candidates"]
+        assert gc["candidates"] > 50 * gc["diffuse_hits"]  # the buckets really are crowded
