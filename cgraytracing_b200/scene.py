@@ -160,6 +160,15 @@ def preset(name: str, max_tris: Optional[int] = None) -> SceneDesc:
         s.add_sphere((10.0, -20.0, 60), 7, (1.0, 1.0, 1.0), 0.8, 0.0)
         s.add_sphere((10.0, -20.0, 30), 7, (1.0, 1.0, 1.0), 0.8, 0.5)
         _walls(s, tex)
+    elif name == "c1_mirror":
+        # c1_spheres plus a mirror sphere INSIDE the room, so that the mirror branch of trace() (main.cpp:129-134) is reached by eye
+        # rays and photons: the only mirror of main.cpp:288-290, Sphere((10,-20,60),7,...,0.8,0), sits behind the back wall (z = 40)
+        tex = _floor_texture(s, "ChessBoard", False)
+        s.add_sphere((-15.0, -20.0, 60), 10, (0.3, 0.3, 0.3), 0.0, 0.0)
+        s.add_sphere((10.0, -20.0, 60), 7, (1.0, 1.0, 1.0), 0.8, 0.0)
+        s.add_sphere((10.0, -20.0, 30), 7, (1.0, 1.0, 1.0), 0.8, 0.5)
+        s.add_sphere((-8.0, -13.0, 25), 7, (0.9, 0.8, 0.7), 0.8, 0.0)
+        _walls(s, tex)
     elif name == "c2_bunny_chess":
         # main.cpp:293 glass bunny (type 0) + chessboard floor
         tex = _floor_texture(s, "ChessBoard", False)
@@ -182,7 +191,7 @@ def preset(name: str, max_tris: Optional[int] = None) -> SceneDesc:
     return s
 
 
-PRESETS = ["default_bump", "c1_spheres_bezier", "c1_spheres", "c2_bunny_chess", "c3_dragon_glass", "c4_bump_dof", "walls_only"]
+PRESETS = ["default_bump", "c1_spheres_bezier", "c1_spheres", "c1_mirror", "c2_bunny_chess", "c3_dragon_glass", "c4_bump_dof", "walls_only"]
 
 
 @dataclass

@@ -188,8 +188,12 @@ class Oracle:
     def trace(self, org, dir, flux, adj, flag, x=0, y=0, path=0):
         self.L.orc_trace(self.h, _p(_d(org), c_dp), _p(_d(dir), c_dp), _p(_d(flux), c_dp), _p(_d(adj), c_dp), int(flag), x, y, C.c_uint64(path))
 
-    def eye_pass(self, y0=0, y1=-1):
-        self.L.orc_eye_pass(self.h, y0, y1)
+    def eye_pass(self, y0=0, y1=-1, nthreads=1):
+        """nthreads > 1 (Philox mode): rows traced in parallel, merged in the reference's creation order — same table."""
+        if nthreads > 1:
+            self.L.orc_eye_pass_mt(self.h, y0, y1, int(nthreads))
+        else:
+            self.L.orc_eye_pass(self.h, y0, y1)
 
     def num_hitpoints(self):
         return int(self.L.orc_num_hitpoints(self.h))
@@ -248,7 +252,12 @@ class Oracle:
         return {n: int(getattr(k, n)) for n, _ in OrcCounters._fields_}
 
     def max_threads(self):
-        return int(self.L.orc_max_threads())
+        """Host threads the oracle may use: the CPUs this process may run on, NOT omp_get_max_threads() — launchers such as
+        torch.distributed.run export OMP_NUM_THREADS=1 into every rank, which would silently time the CPU arm on one core."""
+        try:
+            return max(1, len(os.sched_getaffinity(0)))
+        except AttributeError:
+            return max(1, os.cpu_count() or 1)
 
 
 def hash_keys(pos, hashsize, celllength_in):

@@ -301,6 +301,45 @@ int orc_eye_pass(void *c_, int y0, int y1) {
     c->index();
     return 0;
 }
+// The same eye pass with the rows traced by `nthreads` OpenMP threads (Philox mode only: every path re-keys its own stream, so the
+// result does not depend on who traces it). Each block of rows collects its hitpoints in creation order; the blocks are then inserted
+// in row order with consecutive sequence numbers — exactly the table the sequential loop of main.cpp:185-219 builds.
+int orc_eye_pass_mt(void *c_, int y0, int y1, int nthreads) {
+    Ctx *c = (Ctx *)c_;
+    if (c->libc_mode || nthreads <= 1) return orc_eye_pass(c_, y0, y1);
+#ifdef _OPENMP
+    Renderer &R = c->R;
+    if (y1 < 0) y1 = R.cfg.height;
+    if (!R.htable) R.htable = new Hashtable(R.cfg.hashsize, 200.0 / R.cfg.height);
+    const int rows = y1 - y0, block = 8, nblocks = (rows + block - 1) / block;
+    std::vector<std::vector<Hitpoint>> sinks((size_t)(nblocks > 0 ? nblocks : 0));
+    std::vector<Counters> part((size_t)nthreads);
+    std::vector<KDCounters> kpart((size_t)nthreads);
+#pragma omp parallel num_threads(nthreads)
+    {
+        Renderer w = R.worker();
+        Rng rng = Rng::philox(R.cfg.seed, 0, 0, 0);
+#pragma omp for schedule(dynamic, 1)
+        for (int b = 0; b < nblocks; b++) {
+            w.sink = &sinks[(size_t)b];
+            const int r0 = y0 + b * block, r1 = (r0 + block < y1) ? r0 + block : y1;
+            w.eye_pass(rng, r0, r1);
+        }
+        part[omp_get_thread_num()] = w.ctr;
+        kpart[omp_get_thread_num()] = w.kdc;
+    }
+    for (auto &kp : kpart) { R.kdc.node_visits += kp.node_visits; R.kdc.tri_tests += kp.tri_tests; }
+    for (auto &p : part) { R.ctr.eye_segments += p.eye_segments; R.ctr.misses += p.misses; }
+    for (auto &sk : sinks) {
+        for (auto &hp : sk) { hp.seq = R.next_seq++; R.htable->insert(hp); }
+        std::vector<Hitpoint>().swap(sk);
+    }
+    c->index();
+    return 0;
+#else
+    return orc_eye_pass(c_, y0, y1);
+#endif
+}
 int64_t orc_num_hitpoints(void *c_) { Ctx *c = (Ctx *)c_; c->index(); return (int64_t)c->canon.size(); }
 
 // Canonical order (buckets ascending, insertion order inside a bucket; main.cpp:252-254). Any pointer may be NULL.

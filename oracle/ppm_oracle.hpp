@@ -882,6 +882,9 @@ struct Renderer {
     KDCounters kdc;
     uint32_t next_seq = 0;
     bool owns_htable = true;
+    // Oracle-only: when set, the eye pass appends its hitpoints here (creation order) instead of inserting them, so that row blocks can be
+    // traced by several threads and merged afterwards in the reference's creation order (main.cpp:185-187: h outer, w inner).
+    std::vector<Hitpoint> *sink = nullptr;
 
     ~Renderer() { if (owns_htable) delete htable; }
     // A shallow per-thread view (own counters, shared scene and hitpoints) for the OpenMP photon loop.
@@ -966,7 +969,8 @@ struct Renderer {
                 hp.seq = next_seq++;
                 hp.code = dfs_code & 15u;
                 hp.path = path;
-                htable->insert(hp);
+                if (sink) sink->push_back(hp);
+                else htable->insert(hp);
             } else {  // main.cpp:101-128
                 ctr.diffuse_hits++;
                 int ix, iy, iz;
