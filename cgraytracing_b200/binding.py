@@ -27,7 +27,7 @@ ABI_SYMBOLS = [
     "cgrt_count_traversal", "cgrt_eye_pass", "cgrt_export_hitpoints_dev", "cgrt_import_hitpoints_dev", "cgrt_build_grid", "cgrt_photon_pass",
     "cgrt_accum_dev", "cgrt_allreduce_accum", "cgrt_round_update", "cgrt_gather_image", "cgrt_num_hitpoints", "cgrt_download_hitpoints",
     "cgrt_download_accum", "cgrt_download_grid", "cgrt_get_counters", "cgrt_get_timings", "cgrt_set_counting", "cgrt_set_profiling", "cgrt_set_culling", "cgrt_set_overlap", "cgrt_average_u8", "cgrt_average_f64",
-    "cgrt_check_guards",
+    "cgrt_check_guards", "cgrt_release_cached_memory",
 ]
 
 
@@ -276,12 +276,15 @@ class Context:
         self._ck(self.L.cgrt_num_hitpoints(self.h, C.byref(n)))
         return n.value
 
-    def download_hitpoints(self):
+    def download_hitpoints(self, fields=None):
+        """Canonical order. `fields`: subset of the keys to fetch (default all) — the others are passed as NULL."""
         n = self.num_hitpoints()
-        o = dict(pos=np.zeros((n, 3)), normal=np.zeros((n, 3)), f=np.zeros((n, 3)), flux=np.zeros((n, 3)), r2=np.zeros(n),
-                 n=np.zeros(n, np.int32), hw=np.zeros((n, 2), np.int32), key=np.zeros(n, np.uint32), seq=np.zeros(n, np.uint32))
-        self._ck(self.L.cgrt_download_hitpoints(self.h, _p(o["pos"], c_dp), _p(o["normal"], c_dp), _p(o["f"], c_dp), _p(o["flux"], c_dp), _p(o["r2"], c_dp),
-                                                _p(o["n"], c_ip), _p(o["hw"], c_ip), _p(o["key"], c_up), _p(o["seq"], c_up)))
+        spec = dict(pos=((n, 3), np.float64), normal=((n, 3), np.float64), f=((n, 3), np.float64), flux=((n, 3), np.float64), r2=((n,), np.float64),
+                    n=((n,), np.int32), hw=((n, 2), np.int32), key=((n,), np.uint32), seq=((n,), np.uint32))
+        o = {k: np.zeros(sh, dt) for k, (sh, dt) in spec.items() if fields is None or k in fields}
+        g = o.get
+        self._ck(self.L.cgrt_download_hitpoints(self.h, _p(g("pos"), c_dp), _p(g("normal"), c_dp), _p(g("f"), c_dp), _p(g("flux"), c_dp), _p(g("r2"), c_dp),
+                                                _p(g("n"), c_ip), _p(g("hw"), c_ip), _p(g("key"), c_up), _p(g("seq"), c_up)))
         return o
 
     def download_accum(self):
@@ -313,6 +316,13 @@ class Context:
         """Damaged fence bytes so far (only meaningful when the process was started with CGRT_GUARD=1)."""
         n = C.c_uint64(0)
         self._ck(self.L.cgrt_check_guards(self.h, C.byref(n)))
+        return int(n.value)
+
+    @staticmethod
+    def release_cached_memory(device=-1) -> int:
+        """cudaFree the large buffers the library parked for later contexts (-1: every device). -> bytes released"""
+        n = C.c_uint64(0)
+        load_library().cgrt_release_cached_memory(int(device), C.byref(n))
         return int(n.value)
 
     def set_profiling(self, on=True):

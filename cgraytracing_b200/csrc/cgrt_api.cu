@@ -65,8 +65,47 @@ void *arena_take(int device, size_t bytes) {
         }
     }
     void *p = nullptr;
-    if (cudaMalloc(&p, bytes) != cudaSuccess) { cudaGetLastError(); return nullptr; }
-    return p;
+    if (cudaMalloc(&p, bytes) == cudaSuccess) return p;
+    cudaGetLastError();
+    // Out of memory while blocks of other sizes sit parked: hand them back to the driver, largest first, until the request fits.
+    for (;;) {
+        void *victim = nullptr;
+        {
+            std::lock_guard<std::mutex> lk(g_arena_mutex);
+            size_t big = g_arena.size();
+            for (size_t i = 0; i < g_arena.size(); i++)
+                if (g_arena[i].device == device && (big == g_arena.size() || g_arena[i].bytes > g_arena[big].bytes)) big = i;
+            if (big == g_arena.size()) return nullptr;  // nothing left to release: genuinely out of memory
+            victim = g_arena[big].ptr;
+            g_arena.erase(g_arena.begin() + (long)big);
+        }
+        cudaFree(victim);
+        if (cudaMalloc(&p, bytes) == cudaSuccess) return p;
+        cudaGetLastError();
+    }
+}
+// bytes parked for `device` (the photon pass sizes its launches from free + parked memory)
+size_t arena_held(int device) {
+    std::lock_guard<std::mutex> lk(g_arena_mutex);
+    size_t held = 0;
+    for (const ArenaBlock &b : g_arena) held += b.device == device ? b.bytes : 0;
+    return held;
+}
+// cudaFree every parked block of `device` (all devices when device < 0) -> bytes released
+size_t arena_trim(int device) {
+    std::vector<ArenaBlock> victims;
+    {
+        std::lock_guard<std::mutex> lk(g_arena_mutex);
+        for (size_t i = 0; i < g_arena.size();)
+            if (device < 0 || g_arena[i].device == device) { victims.push_back(g_arena[i]); g_arena.erase(g_arena.begin() + (long)i); }
+            else i++;
+    }
+    size_t freed = 0;
+    int cur = 0;
+    cudaGetDevice(&cur);
+    for (const ArenaBlock &b : victims) { cudaSetDevice(b.device); cudaFree(b.ptr); freed += b.bytes; }
+    cudaSetDevice(cur);
+    return freed;
 }
 void arena_give(int device, size_t bytes, void *p) {
     if (!p) return;
@@ -462,10 +501,17 @@ int ensure_photon_buffers(cgrt_ctx *ctx, size_t photons, size_t slots) {
             big_give(ctx, b.cap * sizeof(uint32_t), b.keys);
             big_give(ctx, b.cap * sizeof(uint32_t), b.perm);
         }
-        b.rec = (DepositRec *)big_take(ctx, slots * sizeof(DepositRec));
-        b.keys = (uint32_t *)big_take(ctx, slots * sizeof(uint32_t));
-        b.perm = (uint32_t *)big_take(ctx, slots * sizeof(uint32_t));
-        if (!b.rec || !b.keys || !b.perm) FAIL(CGRT_ERR_CUDA, "out of device memory for the deposit tables");
+        b.cap = 0; b.rec = nullptr; b.keys = nullptr; b.perm = nullptr;  // nothing dangles if a block below cannot be had
+        DepositRec *nrec = (DepositRec *)big_take(ctx, slots * sizeof(DepositRec));
+        uint32_t *nkeys = (uint32_t *)big_take(ctx, slots * sizeof(uint32_t));
+        uint32_t *nperm = (uint32_t *)big_take(ctx, slots * sizeof(uint32_t));
+        if (!nrec || !nkeys || !nperm) {
+            big_give(ctx, slots * sizeof(DepositRec), nrec);
+            big_give(ctx, slots * sizeof(uint32_t), nkeys);
+            big_give(ctx, slots * sizeof(uint32_t), nperm);
+            FAIL(CGRT_ERR_CUDA, "out of device memory for the deposit tables");
+        }
+        b.rec = nrec; b.keys = nkeys; b.perm = nperm;
         b.cap = slots;
         b.drained_valid = false;
         fresh = true;
@@ -474,8 +520,15 @@ int ensure_photon_buffers(cgrt_ctx *ctx, size_t photons, size_t slots) {
         CK(cudaStreamSynchronize(ctx->tstream));
         for (int k = 0; k < 2; k++) {
             if (ctx->pq_cap) big_give(ctx, ctx->pq_cap * sizeof(PhotonState), ctx->pq[k]);
+            ctx->pq[k] = nullptr;
+        }
+        ctx->pq_cap = 0;
+        for (int k = 0; k < 2; k++) {
             ctx->pq[k] = (PhotonState *)big_take(ctx, photons * sizeof(PhotonState));
-            if (!ctx->pq[k]) FAIL(CGRT_ERR_CUDA, "out of device memory for the photon queues");
+            if (!ctx->pq[k]) {
+                if (k == 1) { big_give(ctx, photons * sizeof(PhotonState), ctx->pq[0]); ctx->pq[0] = nullptr; }
+                FAIL(CGRT_ERR_CUDA, "out of device memory for the photon queues");
+            }
         }
         ctx->pq_cap = photons;
         fresh = true;
@@ -1112,7 +1165,11 @@ int cgrt_photon_pass(cgrt_ctx *ctx, uint64_t first, uint64_t count) {
         size_t free_b = 0, total_b = 0;
         CK(cudaMemGetInfo(&free_b, &total_b));
         const size_t per_photon = (size_t)P.max_depth * (sizeof(DepositRec) + 2 * sizeof(uint32_t)) * (ctx->overlap ? 2 : 1) + 2 * sizeof(PhotonState);
-        chunk = (total_b / 10 * 6) / per_photon;
+        // what this context can actually get: free memory plus the blocks the arena holds for this device (a parked block is either
+        // reused as it is or released on demand by arena_take), not the device's total — other contexts and frameworks share the GPU
+        const size_t avail_b = free_b + arena_held(ctx->device);
+        (void)total_b;
+        chunk = (avail_b / 10 * 6) / per_photon;
         chunk &= ~(((size_t)1 << 20) - 1);
         if (chunk > ((size_t)128 << 20)) chunk = (size_t)128 << 20;
         if (chunk < ((size_t)1 << 20)) chunk = (size_t)1 << 20;
@@ -1302,7 +1359,8 @@ int cgrt_gather_image(cgrt_ctx *ctx, double n_emitted, double *rgb, uint8_t *rgb
     uint8_t *d_rgb8 = nullptr;
     CKS(dalloc(ctx, &d_rgb, npix * 3));
     if (rgb8) CKS(dalloc(ctx, &d_rgb8, npix * 3));
-    image_gather_kernel<<<nblk(npix, 256), 256, 0, ctx->stream>>>(P.width, P.height, n_emitted, ctx->pix_start, ctx->pix_perm, ctx->A.hot, ctx->A.flux,
+    // main.cpp:256 divides by num_photon*num_threads*num_of_samples: the caller states the photons, the samples factor comes from the config
+    image_gather_kernel<<<nblk(npix, 256), 256, 0, ctx->stream>>>(P.width, P.height, n_emitted * (double)P.samples, ctx->pix_start, ctx->pix_perm, ctx->A.hot, ctx->A.flux,
                                                                   d_rgb, d_rgb8);
     ctx->launches++;
     CK(cudaGetLastError());
@@ -1459,6 +1517,12 @@ int cgrt_set_overlap(cgrt_ctx *ctx, int on) {
     CK(cudaStreamSynchronize(ctx->stream));
     ctx->overlap = on != 0;
     ctx->auto_chunk = 0;  // two deposit tables: the chunk is sized again
+    return CGRT_OK;
+}
+
+int cgrt_release_cached_memory(int device, uint64_t *bytes_released) {
+    const size_t freed = arena_trim(device);
+    if (bytes_released) *bytes_released = (uint64_t)freed;
     return CGRT_OK;
 }
 

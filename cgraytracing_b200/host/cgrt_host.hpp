@@ -324,7 +324,7 @@ inline Image render(const std::vector<Object *> &objs, const RenderOptions &opt 
     img.width = opt.width; img.height = opt.height;
     img.rgb.resize((size_t)opt.width * opt.height * 3);
     img.rgb8.resize(img.rgb.size());
-    c.check(cgrt_gather_image(c.get(), (double)total * opt.num_of_samples, img.rgb.data(), img.rgb8.data()));  // main.cpp:252-258, 403-411
+    c.check(cgrt_gather_image(c.get(), (double)total, img.rgb.data(), img.rgb8.data()));  // main.cpp:252-258 (the library applies num_of_samples), 403-411
     if (counters) c.check(cgrt_get_counters(c.get(), counters));
     return img;
 }
@@ -347,6 +347,7 @@ inline std::vector<double> read_mesh_asset(const std::string &path, double a, co
     char magic[8];
     int32_t nn[2];
     if (!in.read(magic, 8) || std::string(magic, 8) != "CGRTMSH1" || !in.read((char *)nn, 8)) throw Error(CGRT_ERR_INVALID, "not a .cgrtmesh file: " + path);
+    if (nn[0] < 0 || nn[1] < 0) throw Error(CGRT_ERR_INVALID, "corrupt mesh header: " + path);
     std::vector<double> v((size_t)nn[0] * 3);
     std::vector<int32_t> f((size_t)nn[1] * 3);
     if (!in.read((char *)v.data(), (std::streamsize)(v.size() * 8)) || !in.read((char *)f.data(), (std::streamsize)(f.size() * 4)))
@@ -354,6 +355,7 @@ inline std::vector<double> read_mesh_asset(const std::string &path, double a, co
     std::vector<double> tri9;
     tri9.reserve(f.size() * 3);
     for (int32_t id : f) {
+        if (id < 0 || id >= nn[0]) throw Error(CGRT_ERR_INVALID, "mesh face index out of range: " + path);
         Vec3 p = Vec3(v[(size_t)id * 3], v[(size_t)id * 3 + 1], -v[(size_t)id * 3 + 2]) * a + b;
         tri9.push_back(p.x); tri9.push_back(p.y); tri9.push_back(p.z);
     }

@@ -29,6 +29,8 @@ def read_mesh_asset(path: str):
     nv, nf = struct.unpack_from("<ii", raw, 8)
     v = np.frombuffer(raw, dtype="<f8", count=nv * 3, offset=16).reshape(nv, 3)
     f = np.frombuffer(raw, dtype="<i4", count=nf * 3, offset=16 + nv * 24).reshape(nf, 3)
+    if nf and (f.min() < 0 or f.max() >= nv):
+        raise ValueError(f"{path}: face index out of range")
     return v.copy(), f.copy()
 
 

@@ -130,7 +130,9 @@ int cgrt_accum_dev(cgrt_ctx *ctx, void **ptr_dev, int64_t *n_doubles);
 int cgrt_allreduce_accum(cgrt_ctx *ctx, void *nccl_comm);
 /* Per-round radius/flux update (main.cpp:119-122 in its batched form, SURVEY Q1 "U2"), then clears the accumulators. */
 int cgrt_round_update(cgrt_ctx *ctx);
-/* main.cpp:252-258 (+ :403-411 when rgb8 != NULL: tone map, gamma, vertical flip). rgb: H*W*3 fp64, row h = image[h]. */
+/* main.cpp:252-258 (+ :403-411 when rgb8 != NULL: tone map, gamma, vertical flip). rgb: H*W*3 fp64, row h = image[h].
+ * n_emitted = photons traced so far, the reference's num_photon*num_threads; the third factor of main.cpp:256, num_of_samples, is taken
+ * from cgrt_config, so that every caller normalises a multi-sample image the same way. */
 int cgrt_gather_image(cgrt_ctx *ctx, double n_emitted, double *rgb, uint8_t *rgb8);
 
 /* ---- multi-run averaging (average.cpp:19-65), the reference's way of combining separately rendered images ------------ */
@@ -172,6 +174,10 @@ int cgrt_get_timings(cgrt_ctx *ctx, double ms[12]);
  * environment every device buffer of a context sits between two 4 KiB fences of a known byte pattern. Synchronises and returns in
  * *damaged the number of fence bytes kernels have overwritten so far (released buffers included); 0 when the mode is off. */
 int cgrt_check_guards(cgrt_ctx *ctx, uint64_t *damaged);
+/* The library keeps the large device buffers of destroyed contexts (deposit tables, photon queues, ray queues) parked per device and
+ * hands them to the next context: a render() creates and destroys one. Parked blocks are released automatically when an allocation
+ * would otherwise fail; this call releases them now (device < 0: all devices). bytes_released may be NULL. */
+int cgrt_release_cached_memory(int device, uint64_t *bytes_released);
 
 #ifdef __cplusplus
 }

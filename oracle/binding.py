@@ -198,14 +198,16 @@ class Oracle:
     def num_hitpoints(self):
         return int(self.L.orc_num_hitpoints(self.h))
 
-    def download_hitpoints(self):
+    def download_hitpoints(self, fields=None):
         n = self.num_hitpoints()
-        o = dict(pos=np.zeros((n, 3)), normal=np.zeros((n, 3)), f=np.zeros((n, 3)), flux=np.zeros((n, 3)), r2=np.zeros(n),
-                 n=np.zeros(n, np.int32), hw=np.zeros((n, 2), np.int32), key=np.zeros(n, np.uint32), seq=np.zeros(n, np.uint32),
-                 code=np.zeros(n, np.uint32), path=np.zeros(n, np.uint64))
-        self.L.orc_download_hitpoints(self.h, _p(o["pos"], c_dp), _p(o["normal"], c_dp), _p(o["f"], c_dp), _p(o["flux"], c_dp),
-                                      _p(o["r2"], c_dp), _p(o["n"], c_ip), _p(o["hw"], c_ip), _p(o["key"], c_up), _p(o["seq"], c_up),
-                                      _p(o["code"], c_up), _p(o["path"], c_u64p))
+        spec = dict(pos=((n, 3), np.float64), normal=((n, 3), np.float64), f=((n, 3), np.float64), flux=((n, 3), np.float64), r2=((n,), np.float64),
+                    n=((n,), np.int32), hw=((n, 2), np.int32), key=((n,), np.uint32), seq=((n,), np.uint32), code=((n,), np.uint32),
+                    path=((n,), np.uint64))
+        o = {k: np.zeros(sh, dt) for k, (sh, dt) in spec.items() if fields is None or k in fields}
+        g = o.get
+        self.L.orc_download_hitpoints(self.h, _p(g("pos"), c_dp), _p(g("normal"), c_dp), _p(g("f"), c_dp), _p(g("flux"), c_dp),
+                                      _p(g("r2"), c_dp), _p(g("n"), c_ip), _p(g("hw"), c_ip), _p(g("key"), c_up), _p(g("seq"), c_up),
+                                      _p(g("code"), c_up), _p(g("path"), c_u64p))
         return o
 
     def download_accum(self):

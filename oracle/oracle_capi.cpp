@@ -473,7 +473,8 @@ int orc_round_update(void *c_) { ((Ctx *)c_)->R.round_update(); return 0; }
 int orc_gather_image(void *c_, double n_emitted, double *rgb) {
     Ctx *c = (Ctx *)c_;
     std::vector<Vec3> img;
-    c->R.gather_image(n_emitted, img);
+    // n_emitted = num_photon*num_threads; the num_of_samples factor of main.cpp:256 comes from the config (same convention as cgrt_gather_image)
+    c->R.gather_image(n_emitted * (double)c->R.cfg.num_of_samples, img);
     for (size_t i = 0; i < img.size(); i++) st3(rgb + 3 * i, img[i]);
     return 0;
 }

@@ -468,3 +468,22 @@ def test_colliding_buckets_are_listed_like_the_reference(gpu, oracle_lib, hashsi
         gc, oc = g.counters(), o.counters()
         assert gc["deposits"] == oc["deposits"] and gc["candidates"] == oc["candidates"]
         assert gc["candidates"] > 50 * gc["diffuse_hits"]  # the buckets really are crowded
+
+
+def test_multisample_image_is_normalised_like_the_reference(gpu, oracle_lib):
+    """main.cpp:256 divides by num_photon*num_threads*num_of_samples. Callers state the photons; the samples factor is applied by the
+    library (and by the oracle) from the config, so that no entry point can produce a picture num_of_samples times too bright."""
+    s = gpu.preset("c4_bump_dof", max_tris=None)
+    cfg = gpu.RenderConfig(width=96, height=64, use_dof=1, num_of_samples=4)
+    N = 40000
+    o = oracle_lib.Oracle(s, cfg)
+    o.eye_pass(); o.photon_pass(0, N, o.max_threads()); o.round_update()
+    with gpu.Context(0, s, cfg) as g:
+        g.eye_pass(); g.build_grid(); g.photon_pass(0, N); g.round_update()
+        img = g.gather_image(float(N))
+        hp = g.download_hitpoints(fields=("flux", "r2", "hw"))
+    want = np.zeros_like(img)
+    v = hp["flux"] * (1.0 / (3.14159265358979 * hp["r2"] * float(N) * 4.0))[:, None]  # the reference's normaliser, written out
+    np.add.at(want, (hp["hw"][:, 0], hp["hw"][:, 1]), v)
+    assert img.mean() > 0.01 and np.allclose(img, want, rtol=1e-12, atol=1e-15)
+    assert np.allclose(img, o.gather_image(float(N)), rtol=1e-9, atol=1e-12)
