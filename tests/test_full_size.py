@@ -13,6 +13,8 @@ pinned bit-exact to the compiled reference in tests/test_oracle_vs_ref.py, tests
 import numpy as np
 import pytest
 
+from tests.util import assert_flux_close
+
 pytestmark = pytest.mark.gpu
 
 CASES = {
@@ -21,8 +23,7 @@ CASES = {
     "c4": ("c4_bump_dof", 1920, 1080, 1000001, 1, 4, 1 << 20),
     "c5": ("c3_dragon_glass", 4096, 4096, 16777259, 0, 1, 1 << 20),
 }
-F64_RTOL = 1e-9      # fp64 atomics: only the order of the additions differs
-F32_U = 2.0 ** -24   # float accumulators: unit round-off
+
 _cache = {}
 
 
@@ -69,11 +70,4 @@ def test_full_size_equals_oracle(gpu, oracle_lib, case, accum):
         assert gc[k] == octr[k], k
     assert np.array_equal(m.astype(np.int64), om.astype(np.int64))   # accepted photons per hitpoint: exact in both accumulator types
     assert int(m.sum()) == gc["deposits"] > N
-    err = np.abs(df - odf)
-    if accum == 0:
-        assert np.all(err <= F64_RTOL * np.abs(odf) + 1e-9)
-    else:
-        # every deposit is positive: |float sum - exact sum| <= (m - 1 + roundings of one term) * u * sum, whatever the order
-        bound = (om[:, None].astype(np.float64) + 8.0) * F32_U * np.abs(odf) + 1e-6
-        assert np.all(err <= bound), float((err / np.maximum(bound, 1e-300)).max())
-        assert np.median(err[odf > 0] / odf[odf > 0]) < 2e-7  # and typically a few ulp
+    assert_flux_close(df, odf, om, accum)

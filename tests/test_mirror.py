@@ -12,7 +12,7 @@ import numpy as np
 import pytest
 
 from cgraytracing_b200 import RenderConfig, preset
-from tests.util import camera_rays
+from tests.util import assert_flux_close, camera_rays
 
 GOLDEN = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "ref_mirror.npz")
 MIRROR_ID = 3  # the fourth sphere of c1_mirror
@@ -128,12 +128,11 @@ def test_gpu_mirror_rounds_equal_the_oracle(gpu, oracle_lib, accum):
         assert len(a["pos"]) == len(b["pos"]) > W * H
         for k in ("key", "hw", "pos", "normal", "f", "r2"):
             assert np.array_equal(a[k], b[k]), k
-        rtol, atol = (1e-9, 1e-12) if accum == 0 else (1e-5, 1e-4)
         for rnd in range(2):
             g.photon_pass(rnd * NPH, NPH); o.photon_pass(rnd * NPH, NPH, o.max_threads())
             df, m = g.download_accum(); odf, om = o.download_accum()
             assert np.array_equal(m.astype(np.int64), om.astype(np.int64))
-            assert np.allclose(df, odf, rtol=rtol, atol=atol)
+            assert_flux_close(df, odf, om, accum)
             g.round_update(); o.round_update()
         gc, oc = g.counters(), o.counters()
         for k in ("photon_segments", "diffuse_hits", "deposits"):
@@ -143,4 +142,4 @@ def test_gpu_mirror_rounds_equal_the_oracle(gpu, oracle_lib, accum):
         # hitpoints seen through the mirror receive photons too
         tinted = _through_mirror(b["f"])
         assert tinted.sum() > 500 and b["n"][tinted].sum() > 100
-        assert np.allclose(g.gather_image(2.0 * NPH), o.gather_image(2.0 * NPH), rtol=rtol, atol=atol * 1e-2)
+        assert np.allclose(g.gather_image(2.0 * NPH), o.gather_image(2.0 * NPH), rtol=1e-9 if accum == 0 else 1e-4, atol=1e-12 if accum == 0 else 1e-6)

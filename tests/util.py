@@ -27,3 +27,18 @@ def rel_err(a, b):
     a = np.asarray(a, dtype=np.float64)
     b = np.asarray(b, dtype=np.float64)
     return np.abs(a - b) / np.maximum(np.abs(b), 1e-300)
+
+
+def assert_flux_close(df, odf, om, accum):
+    """Per-hitpoint flux accumulators of the GPU (df) against the oracle's (odf, fp64), om = accepted photons per hitpoint.
+    accum 0 (fp64 atomics): only the order of the additions differs -> 1e-9 relative.
+    accum 1 (float `red` accumulators): every deposit is positive, so summing m of them in float in ANY order is within
+    (m - 1 + roundings of one term) * 2^-24 of the exact sum, relative — the worst-case bound of recursive summation."""
+    err = np.abs(np.asarray(df, np.float64) - odf)
+    if accum == 0:
+        assert np.all(err <= 1e-9 * np.abs(odf) + 1e-9), float(err.max())
+    else:
+        bound = (np.asarray(om, np.float64)[:, None] + 8.0) * 2.0 ** -24 * np.abs(odf) + 1e-6
+        assert np.all(err <= bound), float((err / bound).max())
+        pos = odf > 0
+        assert np.median(err[pos] / odf[pos]) < 5e-7  # and typically a few ulp
