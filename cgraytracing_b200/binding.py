@@ -27,7 +27,8 @@ ABI_SYMBOLS = [
     "cgrt_count_traversal", "cgrt_eye_pass", "cgrt_export_hitpoints_dev", "cgrt_import_hitpoints_dev", "cgrt_build_grid", "cgrt_photon_pass",
     "cgrt_accum_dev", "cgrt_allreduce_accum", "cgrt_round_update", "cgrt_gather_image", "cgrt_num_hitpoints", "cgrt_download_hitpoints",
     "cgrt_download_accum", "cgrt_download_grid", "cgrt_get_counters", "cgrt_get_timings", "cgrt_set_counting", "cgrt_set_profiling", "cgrt_set_culling", "cgrt_set_overlap", "cgrt_average_u8", "cgrt_average_f64",
-    "cgrt_check_guards", "cgrt_release_cached_memory",
+    "cgrt_check_guards", "cgrt_release_cached_memory", "cgrt_photon_chunk",
+    "cgrt_comm_unique_id", "cgrt_comm_init_rank", "cgrt_comm_init_all", "cgrt_comm_destroy", "cgrt_allgather_hitpoints", "cgrt_set_comm",
 ]
 
 
@@ -42,7 +43,8 @@ class CgrtConfig(C.Structure):
 
 class CgrtCounters(C.Structure):
     _fields_ = [(n, C.c_uint64) for n in (
-        "eye_segments", "photon_segments", "diffuse_hits", "candidates", "deposits", "node_visits", "tri_tests", "hitpoints", "gpu_launches", "gathered_hits", "exact_tests")]
+        "eye_segments", "photon_segments", "diffuse_hits", "candidates", "deposits", "node_visits", "tri_tests", "hitpoints", "gpu_launches", "gathered_hits", "exact_tests",
+        "cell_groups", "staged_candidates")]
 
 
 class CgrtError(RuntimeError):
@@ -325,6 +327,21 @@ class Context:
         load_library().cgrt_release_cached_memory(int(device), C.byref(n))
         return int(n.value)
 
+    def photon_chunk(self) -> int:
+        n = C.c_uint64(0)
+        self._ck(self.L.cgrt_photon_chunk(self.h, C.byref(n)))
+        return int(n.value)
+
+    # -- multi-GPU through the C ABI (NCCL bound at run time)
+    def set_comm(self, comm, world):
+        self._ck(self.L.cgrt_set_comm(self.h, C.c_void_p(comm), int(world)))
+
+    def allgather_hitpoints(self, comm, world):
+        self._ck(self.L.cgrt_allgather_hitpoints(self.h, C.c_void_p(comm), int(world)))
+
+    def allreduce_accum(self, comm):
+        self._ck(self.L.cgrt_allreduce_accum(self.h, C.c_void_p(comm)))
+
     def set_profiling(self, on=True):
         self._ck(self.L.cgrt_set_profiling(self.h, int(on)))
 
@@ -334,3 +351,25 @@ class Context:
         names = ["eye", "grid", "photon_trace", "photon_deposit", "update", "gather", "deposit_sort", "trace_traverse", "trace_continue",
                  "trace_emit", "r10", "r11"]
         return {n: ms[i] for i, n in enumerate(names)}
+
+
+def comm_unique_id() -> bytes:
+    """128-byte ncclUniqueId (make it on rank 0, hand it to every rank)."""
+    buf = C.create_string_buffer(128)
+    rc = load_library().cgrt_comm_unique_id(buf)
+    if rc != 0:
+        raise CgrtError(f"cgrt_comm_unique_id failed with status {rc} (is NCCL loadable?)")
+    return buf.raw
+
+
+def comm_init_rank(device: int, rank: int, world: int, uid: bytes) -> int:
+    """-> ncclComm_t as an integer handle (collective: every rank must call it)."""
+    comm = C.c_void_p()
+    rc = load_library().cgrt_comm_init_rank(int(device), int(rank), int(world), C.c_char_p(uid), C.byref(comm))
+    if rc != 0:
+        raise CgrtError(f"cgrt_comm_init_rank failed with status {rc}")
+    return comm.value
+
+
+def comm_destroy(comm: int) -> None:
+    load_library().cgrt_comm_destroy(C.c_void_p(comm))

@@ -14,9 +14,7 @@
 
 #include "cgrt_passes.cuh"
 
-#ifdef CGRT_WITH_NCCL
-#include <nccl.h>
-#endif
+#include <dlfcn.h>
 
 using namespace cgrt;
 
@@ -116,6 +114,44 @@ void arena_give(int device, size_t bytes, void *p) {
     g_arena.push_back(ArenaBlock{device, bytes, p});
 }
 
+// NCCL is bound at run time, never at link time: the communicator a host hands to cgrt_allreduce_accum must be driven by the SAME
+// NCCL build that created it, and a process may already hold one (a framework's bundled copy). The copy already loaded in the
+// process wins (dlopen with RTLD_NOLOAD finds it by its soname), else the system's libnccl.so.2 is loaded.
+struct NcclUniqueId { char internal[128]; };  // ncclUniqueId (nccl.h: NCCL_UNIQUE_ID_BYTES = 128), passed by value
+struct NcclApi {
+    void *handle = nullptr;
+    int (*GetUniqueId)(NcclUniqueId *) = nullptr;
+    int (*CommInitRank)(void **, int, NcclUniqueId, int) = nullptr;
+    int (*CommInitAll)(void **, int, const int *) = nullptr;
+    int (*CommDestroy)(void *) = nullptr;
+    int (*AllReduce)(const void *, void *, size_t, int, int, void *, cudaStream_t) = nullptr;
+    int (*AllGather)(const void *, void *, size_t, int, void *, cudaStream_t) = nullptr;
+    const char *(*GetErrorString)(int) = nullptr;
+    std::string why;
+    bool ok = false;
+};
+enum { NCCL_UINT8 = 1, NCCL_INT64 = 4, NCCL_FLOAT32 = 7, NCCL_FLOAT64 = 8, NCCL_SUM = 0 };  // ncclDataType_t / ncclRedOp_t values (nccl.h)
+NcclApi &nccl_api() {
+    static NcclApi api;
+    static std::once_flag once;
+    std::call_once(once, [] {
+        const char *names[] = {"libnccl.so.2", "libnccl.so"};
+        for (const char *n : names) if (!api.handle) api.handle = dlopen(n, RTLD_NOW | RTLD_NOLOAD);
+        for (const char *n : names) if (!api.handle) api.handle = dlopen(n, RTLD_NOW | RTLD_GLOBAL);
+        if (!api.handle) { api.why = "libnccl.so.2 not found (dlopen)"; return; }
+        auto sym = [&](const char *n) { void *p = dlsym(api.handle, n); if (!p) api.why = std::string("missing NCCL symbol ") + n; return p; };
+        api.GetUniqueId = (decltype(api.GetUniqueId))sym("ncclGetUniqueId");
+        api.CommInitRank = (decltype(api.CommInitRank))sym("ncclCommInitRank");
+        api.CommInitAll = (decltype(api.CommInitAll))sym("ncclCommInitAll");
+        api.CommDestroy = (decltype(api.CommDestroy))sym("ncclCommDestroy");
+        api.AllReduce = (decltype(api.AllReduce))sym("ncclAllReduce");
+        api.AllGather = (decltype(api.AllGather))sym("ncclAllGather");
+        api.GetErrorString = (decltype(api.GetErrorString))sym("ncclGetErrorString");
+        api.ok = api.why.empty();
+    });
+    return api;
+}
+
 // ping-pong buffers of the radix sort
 template <typename K>
 struct SortScratch {
@@ -176,6 +212,15 @@ struct cgrt_ctx {
     } dep[2];
     unsigned int chunk_seq = 0;
     cudaStream_t tstream = nullptr;
+    // The per-round tail (all-reduce of the accumulators when a communicator is attached, then round_update_kernel) runs on its own stream:
+    // it only has to finish before the NEXT round's sort + deposit, so the next round's trace launches — which never read a radius or an
+    // accumulator — run underneath it. `updated` is what every reader of hitpoint state waits for (join_update).
+    cudaStream_t ustream = nullptr;
+    cudaEvent_t ev_tail = nullptr, ev_updated = nullptr;
+    bool update_pending = false;
+    void *comm = nullptr;   // ncclComm_t attached by cgrt_set_comm (not owned)
+    int comm_world = 1;
+    int sm_count = 148;
     int overlap = 0;  // measured on c3: the two halves slow each other down by more than they overlap (25.3 vs 24.2 ms per round)
     // resident-grid sizes of the persistent photon kernels (SMs x occupancy), so that static striding leaves no tail of late blocks
     unsigned int grid_first = 592, grid_cont = 592, trav_grid = 0;
@@ -224,6 +269,16 @@ namespace {
         return (code);    \
     } while (0)
 
+// Everything that reads or writes hitpoint state on the main stream first waits for the pending per-round update (stream-side wait, the
+// host is not blocked).
+int join_update(cgrt_ctx *ctx) {
+    if (ctx->update_pending) {
+        CK(cudaStreamWaitEvent(ctx->stream, ctx->ev_updated, 0));
+        ctx->update_pending = false;
+    }
+    return 0;
+}
+
 // Small and medium buffers come from the stream-ordered pool (no device-wide sync, memory is reused); buffers of CGRT_ARENA_MIN bytes
 // or more (ray queues, hitpoint records) come from the process-wide arena of plain cudaMalloc blocks: growing the pool by gigabytes
 // was measured at 150-400 ms per context, a cudaMalloc of the same size at a few ms, and a parked block costs nothing.
@@ -237,6 +292,7 @@ bool guard_mode() {
 uint64_t guard_damage(cgrt_ctx *ctx, void *base, size_t bytes) {
     std::vector<unsigned char> h(2 * CGRT_GUARD_BYTES);
     if (ctx->tstream) cudaStreamSynchronize(ctx->tstream);
+    if (ctx->ustream) cudaStreamSynchronize(ctx->ustream);
     cudaStreamSynchronize(ctx->stream);
     cudaMemcpy(h.data(), base, CGRT_GUARD_BYTES, cudaMemcpyDeviceToHost);
     cudaMemcpy(h.data() + CGRT_GUARD_BYTES, (char *)base + CGRT_GUARD_BYTES + bytes, CGRT_GUARD_BYTES, cudaMemcpyDeviceToHost);
@@ -622,7 +678,10 @@ int cgrt_create(int device, cgrt_ctx **out) {
     ctx->device = device;
     {
         int sms = 0;
-        if (cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, device) == cudaSuccess && sms > 0) ctx->deposit_grid = (unsigned int)sms * 8u;
+        if (cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, device) == cudaSuccess && sms > 0) {
+            ctx->sm_count = sms;
+            ctx->deposit_grid = (unsigned int)sms * 8u;
+        }
     }
     {
         int sms = 148, nb = 0;
@@ -650,6 +709,9 @@ int cgrt_create(int device, cgrt_ctx **out) {
         }
     }
     if (cudaStreamCreateWithFlags(&ctx->tstream, cudaStreamNonBlocking) != cudaSuccess ||
+        cudaStreamCreateWithFlags(&ctx->ustream, cudaStreamNonBlocking) != cudaSuccess ||
+        cudaEventCreateWithFlags(&ctx->ev_tail, cudaEventDisableTiming) != cudaSuccess ||
+        cudaEventCreateWithFlags(&ctx->ev_updated, cudaEventDisableTiming) != cudaSuccess ||
         cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking) != cudaSuccess || cudaEventCreate(&ctx->ev[0]) != cudaSuccess ||
         cudaEventCreate(&ctx->ev[1]) != cudaSuccess) {
         delete ctx;
@@ -672,6 +734,7 @@ int cgrt_destroy(cgrt_ctx *ctx) {
     if (!ctx) return CGRT_OK;
     cudaSetDevice(ctx->device);
     if (ctx->tstream) cudaStreamSynchronize(ctx->tstream);
+    if (ctx->ustream) cudaStreamSynchronize(ctx->ustream);
     cudaStreamSynchronize(ctx->stream);
     for (auto &b : ctx->dep) {
         if (b.traced) cudaEventDestroy(b.traced);
@@ -693,8 +756,11 @@ int cgrt_destroy(cgrt_ctx *ctx) {
     cudaStreamSynchronize(ctx->stream);
     if (ctx->ev[0]) cudaEventDestroy(ctx->ev[0]);
     if (ctx->ev[1]) cudaEventDestroy(ctx->ev[1]);
+    if (ctx->ev_tail) cudaEventDestroy(ctx->ev_tail);
+    if (ctx->ev_updated) cudaEventDestroy(ctx->ev_updated);
     if (ctx->stream) cudaStreamDestroy(ctx->stream);
     if (ctx->tstream) cudaStreamDestroy(ctx->tstream);
+    if (ctx->ustream) cudaStreamDestroy(ctx->ustream);
     delete ctx;
     return CGRT_OK;
 }
@@ -721,6 +787,7 @@ int cgrt_get_stream(cgrt_ctx *ctx, void **stream) {
 int cgrt_synchronize(cgrt_ctx *ctx) {
     if (!ctx) return CGRT_ERR_INVALID;
     CK(cudaStreamSynchronize(ctx->tstream));
+    CKS(join_update(ctx));
     CK(cudaStreamSynchronize(ctx->stream));
     if (!ctx->timeline.empty()) {
         for (size_t k = 0; k + 3 < ctx->timeline.size(); k += 4) {
@@ -1179,7 +1246,7 @@ int cgrt_photon_pass(cgrt_ctx *ctx, uint64_t first, uint64_t count) {
     if (first_chunk == 0) return CGRT_OK;
     CKS(ensure_photon_buffers(ctx, first_chunk, first_chunk * (size_t)P.max_depth));
     std::vector<cudaEvent_t> evs;
-    const unsigned int resume_grid = ctx->trav_grid ? ctx->trav_grid : 148u * 8u;  // 8 resident blocks per SM, grid-stride over the queue
+    const unsigned int resume_grid = ctx->trav_grid ? ctx->trav_grid : (unsigned int)ctx->sm_count * 8u;  // 8 resident blocks per SM, grid-stride over the queue
     const bool overlap = ctx->overlap && !ctx->profiling;
     cudaStream_t D = ctx->stream, T = overlap ? ctx->tstream : ctx->stream;
     for (uint64_t done = 0; done < count; done += chunk) {
@@ -1230,7 +1297,8 @@ int cgrt_photon_pass(cgrt_ctx *ctx, uint64_t first, uint64_t count) {
                 }
                 if (ctx->S.nbvh > 0) {
                     // every tree within CGRT_F32_BOUND (all BASELINE scenes): the instantiation without fp64 box arithmetic
-                    bool f32 = getenv("CGRT_TRAV_EXACT") == nullptr;
+                    static const bool trav_exact = getenv("CGRT_TRAV_EXACT") != nullptr;  // dev: force the fp64-slab instantiation
+                    bool f32 = !trav_exact;
                     for (int b = 0; b < ctx->S.nbvh; b++) f32 = f32 && ctx->S.bvh[b].f32_ok;
                     if (ctx->counting) {
                         if (f32) photon_traverse_kernel<true, true><<<resume_grid, 128, 0, T>>>(ctx->S, qin, nin, ctx->d_tc);
@@ -1256,6 +1324,8 @@ int cgrt_photon_pass(cgrt_ctx *ctx, uint64_t first, uint64_t count) {
             CK(cudaStreamWaitEvent(D, B.traced, 0));
         }
         mark(D);
+        // the trace launches above read neither radii nor accumulators; the gather does: the previous round's update must have landed
+        CKS(join_update(ctx));
         if (ctx->nhp > 0) {
             const int nsb = (int)(CGRT_NBINS / (CGRT_SCAN_BLOCK * CGRT_SCAN_ITEMS));
             bin_scan_blocks_kernel<<<nsb, CGRT_SCAN_BLOCK, 0, D>>>(B.hist, B.bsum);
@@ -1312,37 +1382,143 @@ int cgrt_photon_pass(cgrt_ctx *ctx, uint64_t first, uint64_t count) {
 int cgrt_accum_dev(cgrt_ctx *ctx, void **ptr_dev, int64_t *n_elems) {
     if (!ctx || !ptr_dev || !n_elems) return CGRT_ERR_INVALID;
     if (!ctx->grid_built) FAIL(CGRT_ERR_INVALID, "build the grid first");
+    CKS(join_update(ctx));
     *ptr_dev = ctx->acc;
     *n_elems = (int64_t)ctx->nhp * 4;
+    return CGRT_OK;
+}
+
+static int nccl_fail(cgrt_ctx *ctx, int r, const char *what) {
+    NcclApi &N = nccl_api();
+    ctx->err = std::string(what) + ": " + (N.GetErrorString ? N.GetErrorString(r) : "NCCL error");
+    return CGRT_ERR_NCCL;
+}
+static int allreduce_on(cgrt_ctx *ctx, void *comm, cudaStream_t st) {
+    NcclApi &N = nccl_api();
+    if (!N.ok) FAIL(CGRT_ERR_NCCL, "NCCL is not available: " + N.why);
+    if (ctx->nhp == 0) return CGRT_OK;
+    int r = N.AllReduce(ctx->acc, ctx->acc, (size_t)ctx->nhp * 4, ctx->cfg.accum_mode == 0 ? NCCL_FLOAT64 : NCCL_FLOAT32, NCCL_SUM, comm, st);
+    if (r != 0) return nccl_fail(ctx, r, "ncclAllReduce");
+    ctx->launches++;
     return CGRT_OK;
 }
 
 int cgrt_allreduce_accum(cgrt_ctx *ctx, void *nccl_comm) {
     if (!ctx) return CGRT_ERR_INVALID;
     if (!nccl_comm) return CGRT_OK;
-#ifdef CGRT_WITH_NCCL
     if (!ctx->grid_built) FAIL(CGRT_ERR_INVALID, "build the grid first");
-    ncclResult_t r = ncclAllReduce(ctx->acc, ctx->acc, (size_t)ctx->nhp * 4, ctx->cfg.accum_mode == 0 ? ncclDouble : ncclFloat, ncclSum,
-                                   (ncclComm_t)nccl_comm, ctx->stream);
-    if (r != ncclSuccess) FAIL(CGRT_ERR_NCCL, ncclGetErrorString(r));
-    CK(cudaStreamSynchronize(ctx->stream));
+    CK(cudaSetDevice(ctx->device));
+    CKS(join_update(ctx));
+    return allreduce_on(ctx, nccl_comm, ctx->stream);  // asynchronous, ordered on the ctx stream
+}
+
+int cgrt_set_comm(cgrt_ctx *ctx, void *nccl_comm, int world) {
+    if (!ctx || world < 1) return CGRT_ERR_INVALID;
+    if (nccl_comm && !nccl_api().ok) FAIL(CGRT_ERR_NCCL, "NCCL is not available: " + nccl_api().why);
+    CKS(join_update(ctx));
+    ctx->comm = nccl_comm;
+    ctx->comm_world = nccl_comm ? world : 1;
     return CGRT_OK;
-#else
-    FAIL(CGRT_ERR_NCCL, "libcgrt.so was built without NCCL; all-reduce the cgrt_accum_dev buffer from the host framework instead");
-#endif
+}
+
+int cgrt_comm_unique_id(void *id128) {
+    NcclApi &N = nccl_api();
+    if (!id128) return CGRT_ERR_INVALID;
+    if (!N.ok) return CGRT_ERR_NCCL;
+    return N.GetUniqueId((NcclUniqueId *)id128) == 0 ? CGRT_OK : CGRT_ERR_NCCL;
+}
+int cgrt_comm_init_rank(int device, int rank, int world, const void *id128, void **comm) {
+    NcclApi &N = nccl_api();
+    if (!id128 || !comm || world < 1 || rank < 0 || rank >= world) return CGRT_ERR_INVALID;
+    if (!N.ok) return CGRT_ERR_NCCL;
+    if (cudaSetDevice(device) != cudaSuccess) return CGRT_ERR_NO_DEVICE;
+    NcclUniqueId id;
+    memcpy(&id, id128, sizeof id);
+    return N.CommInitRank(comm, world, id, rank) == 0 ? CGRT_OK : CGRT_ERR_NCCL;
+}
+int cgrt_comm_init_all(int n, const int *devices, void **comms) {
+    NcclApi &N = nccl_api();
+    if (n < 1 || !comms) return CGRT_ERR_INVALID;
+    if (!N.ok) return CGRT_ERR_NCCL;
+    return N.CommInitAll(comms, n, devices) == 0 ? CGRT_OK : CGRT_ERR_NCCL;
+}
+int cgrt_comm_destroy(void *comm) {
+    NcclApi &N = nccl_api();
+    if (!comm) return CGRT_OK;
+    if (!N.ok) return CGRT_ERR_NCCL;
+    return N.CommDestroy(comm) == 0 ? CGRT_OK : CGRT_ERR_NCCL;
+}
+
+// Tile-sharded eye pass, the exchange step: every rank contributes the records of its rows; all ranks end up with the same union (rank
+// order = row order, so the union is in creation order; the grid's sort key makes the order irrelevant anyway).
+int cgrt_allgather_hitpoints(cgrt_ctx *ctx, void *nccl_comm, int world) {
+    if (!ctx || world < 1) return CGRT_ERR_INVALID;
+    if (ctx->grid_built) FAIL(CGRT_ERR_INVALID, "grid already built");
+    if (!nccl_comm || world == 1) return CGRT_OK;
+    NcclApi &N = nccl_api();
+    if (!N.ok) FAIL(CGRT_ERR_NCCL, "NCCL is not available: " + N.why);
+    CK(cudaSetDevice(ctx->device));
+    long long *d_counts;
+    CKS(dalloc(ctx, &d_counts, (size_t)world + 1));
+    long long mine = (long long)ctx->hp_count;
+    CK(cudaMemcpyAsync(d_counts + world, &mine, sizeof mine, cudaMemcpyHostToDevice, ctx->stream));
+    int r = N.AllGather(d_counts + world, d_counts, 1, NCCL_INT64, nccl_comm, ctx->stream);
+    if (r != 0) return nccl_fail(ctx, r, "ncclAllGather(counts)");
+    std::vector<long long> counts((size_t)world);
+    CK(cudaMemcpyAsync(counts.data(), d_counts, sizeof(long long) * world, cudaMemcpyDeviceToHost, ctx->stream));
+    CK(cudaStreamSynchronize(ctx->stream));
+    long long cap = 0, total = 0;
+    for (long long c : counts) { cap = c > cap ? c : cap; total += c; }
+    if (total >= (1ll << 32)) FAIL(CGRT_ERR_CAPACITY, "more than 2^32 hitpoints");
+    const size_t rec_bytes = (size_t)CGRT_HP_RECORD_DOUBLES * sizeof(double);
+    double *send, *recv;
+    CKS(dalloc(ctx, &send, (size_t)(cap ? cap : 1) * CGRT_HP_RECORD_DOUBLES));
+    CKS(dalloc(ctx, &recv, (size_t)(cap ? cap : 1) * CGRT_HP_RECORD_DOUBLES * world));
+    if (mine) CK(cudaMemcpyAsync(send, ctx->hp_rec, (size_t)mine * rec_bytes, cudaMemcpyDeviceToDevice, ctx->stream));
+    if (cap) {
+        r = N.AllGather(send, recv, (size_t)cap * rec_bytes, NCCL_UINT8, nccl_comm, ctx->stream);  // equal-size slots, ranks pad to the largest tile
+        if (r != 0) return nccl_fail(ctx, r, "ncclAllGather(records)");
+    }
+    ctx->hp_count = 0;
+    CKS(ensure_hp_capacity(ctx, (size_t)total));
+    size_t at = 0;
+    for (int k = 0; k < world; k++) {
+        if (counts[k]) CK(cudaMemcpyAsync(ctx->hp_rec + at * CGRT_HP_RECORD_DOUBLES, recv + (size_t)k * cap * CGRT_HP_RECORD_DOUBLES, (size_t)counts[k] * rec_bytes,
+                                         cudaMemcpyDeviceToDevice, ctx->stream));
+        at += (size_t)counts[k];
+    }
+    unsigned int c = (unsigned int)total;
+    CK(cudaMemcpyAsync(ctx->d_hp_count, &c, sizeof c, cudaMemcpyHostToDevice, ctx->stream));
+    CK(cudaStreamSynchronize(ctx->stream));
+    ctx->hp_count = c;
+    ctx->launches += 2;
+    CKS(dfree(ctx, send)); CKS(dfree(ctx, recv)); CKS(dfree(ctx, d_counts));
+    return CGRT_OK;
 }
 
 int cgrt_round_update(cgrt_ctx *ctx) {
     if (!ctx) return CGRT_ERR_INVALID;
     if (!ctx->grid_built) FAIL(CGRT_ERR_INVALID, "build the grid first");
     CK(cudaSetDevice(ctx->device));
+    CKS(join_update(ctx));
     PhaseTimer timer(ctx, 4, ctx->profiling != 0);  // asynchronous unless profiling
     unsigned int n = ctx->nhp;
+    // the tail of a round on its own stream (see cgrt_ctx::ustream); on the main stream while profiling so that its events bracket it
+    cudaStream_t U = ctx->profiling ? ctx->stream : ctx->ustream;
+    if (U != ctx->stream) {
+        CK(cudaEventRecord(ctx->ev_tail, ctx->stream));
+        CK(cudaStreamWaitEvent(U, ctx->ev_tail, 0));
+    }
+    if (ctx->comm) CKS(allreduce_on(ctx, ctx->comm, U));
     if (n > 0) {
-        if (ctx->cfg.accum_mode == 0) round_update_kernel<0><<<nblk(n, 256), 256, 0, ctx->stream>>>(n, ctx->P.alpha, ctx->A, ctx->acc);
-        else round_update_kernel<1><<<nblk(n, 256), 256, 0, ctx->stream>>>(n, ctx->P.alpha, ctx->A, ctx->acc);
+        if (ctx->cfg.accum_mode == 0) round_update_kernel<0><<<nblk(n, 256), 256, 0, U>>>(n, ctx->P.alpha, ctx->A, ctx->acc);
+        else round_update_kernel<1><<<nblk(n, 256), 256, 0, U>>>(n, ctx->P.alpha, ctx->A, ctx->acc);
         ctx->launches++;
         CK(cudaGetLastError());
+    }
+    if (U != ctx->stream) {
+        CK(cudaEventRecord(ctx->ev_updated, U));
+        ctx->update_pending = true;
     }
     timer.stop();
     return CGRT_OK;
@@ -1352,6 +1528,7 @@ int cgrt_gather_image(cgrt_ctx *ctx, double n_emitted, double *rgb, uint8_t *rgb
     if (!ctx || !rgb) return CGRT_ERR_INVALID;
     if (!ctx->grid_built) FAIL(CGRT_ERR_INVALID, "build the grid first");
     CK(cudaSetDevice(ctx->device));
+    CKS(join_update(ctx));
     PhaseTimer timer(ctx, 5);
     const PassParams &P = ctx->P;
     size_t npix = (size_t)P.width * P.height;
@@ -1423,6 +1600,7 @@ int cgrt_download_hitpoints(cgrt_ctx *ctx, double *pos, double *normal, double *
     if (!ctx->grid_built) FAIL(CGRT_ERR_INVALID, "build the grid first");
     size_t m = ctx->nhp;
     if (m == 0) return CGRT_OK;
+    CKS(join_update(ctx));
     CK(cudaStreamSynchronize(ctx->stream));
     std::vector<HpHot> hot(m);
     std::vector<double> tmp(m * 4);
@@ -1452,6 +1630,7 @@ int cgrt_download_accum(cgrt_ctx *ctx, double *dflux, double *mcount) {
     if (!ctx->grid_built) FAIL(CGRT_ERR_INVALID, "build the grid first");
     size_t m = ctx->nhp;
     if (m == 0) return CGRT_OK;
+    CKS(join_update(ctx));
     CK(cudaStreamSynchronize(ctx->stream));
     if (ctx->cfg.accum_mode == 0) {
         std::vector<double> a(m * 4);
@@ -1483,6 +1662,7 @@ int cgrt_get_counters(cgrt_ctx *ctx, cgrt_counters *out) {
     if (!ctx || !out) return CGRT_ERR_INVALID;
     Counters c;
     CK(cudaStreamSynchronize(ctx->tstream));
+    CKS(join_update(ctx));
     CK(cudaStreamSynchronize(ctx->stream));
     CK(cudaMemcpy(&c, ctx->d_ctr, sizeof c, cudaMemcpyDeviceToHost));
     memset(out, 0, sizeof *out);
@@ -1493,6 +1673,8 @@ int cgrt_get_counters(cgrt_ctx *ctx, cgrt_counters *out) {
     out->deposits = c.deposits;
     out->gathered_hits = c.gathered_hits;
     out->exact_tests = c.exact_tests;
+    out->cell_groups = c.cell_groups;
+    out->staged_candidates = c.staged_candidates;
     {
         TravCounters tc;
         CK(cudaMemcpy(&tc, ctx->d_tc, sizeof tc, cudaMemcpyDeviceToHost));
@@ -1523,6 +1705,12 @@ int cgrt_set_overlap(cgrt_ctx *ctx, int on) {
 int cgrt_release_cached_memory(int device, uint64_t *bytes_released) {
     const size_t freed = arena_trim(device);
     if (bytes_released) *bytes_released = (uint64_t)freed;
+    return CGRT_OK;
+}
+
+int cgrt_photon_chunk(cgrt_ctx *ctx, uint64_t *photons_per_launch) {
+    if (!ctx || !photons_per_launch) return CGRT_ERR_INVALID;
+    *photons_per_launch = (uint64_t)(ctx->photon_chunk ? ctx->photon_chunk : ctx->auto_chunk);
     return CGRT_OK;
 }
 

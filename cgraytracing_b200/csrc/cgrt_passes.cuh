@@ -75,6 +75,7 @@ __device__ __forceinline__ void push_ray(const RayQueue &q, unsigned int s, d3 o
 
 struct Counters {
     unsigned long long eye_segments, photon_segments, diffuse_hits, candidates, deposits, gathered_hits, exact_tests;
+    unsigned long long cell_groups, staged_candidates;  // deposit kernel: groups of same-cell hits, bucket entries read for them
 };
 
 // =================================================================================================================
@@ -773,7 +774,7 @@ __global__ void __launch_bounds__(CGRT_DEPOSIT_BLOCK, CGRT_DEPOSIT_MINB) photon_
     uint32_t *queue = queue_all[wib];
     const unsigned int lt = (1u << lane) - 1u;
     unsigned long long cand_total = 0;
-    unsigned int ndep = 0, npair = 0;
+    unsigned int ndep = 0, npair = 0, ngroup = 0, nstaged = 0;
     const int idx = lane / 9, idy = (lane / 3) % 3, idz = lane % 3;  // idx outermost, idz innermost (main.cpp:110-112)
     int qn = 0;
     const size_t n_slots = (size_t)__ldg(n_valid);
@@ -846,6 +847,7 @@ __global__ void __launch_bounds__(CGRT_DEPOSIT_BLOCK, CGRT_DEPOSIT_MINB) photon_
                 const uint32_t excl = incl - cnt;
                 const uint32_t total = __shfl_sync(0xffffffffu, incl, 31);
                 cand_total += (lane == 0) ? (unsigned long long)total * (unsigned int)__popc(grp) : 0ull;
+                if (lane == 0) { ngroup++; nstaged += total; }
                 // the cell of this group as a float box (a hair larger): a candidate whose sphere does not reach the box cannot accept
                 // any hit of the group and is dropped once per group instead of being tested against every hit
                 const float bx0 = (float)(-35.0 + (double)cx * P.celllength), by0 = (float)(-35.0 + (double)cy * P.celllength),
@@ -955,6 +957,8 @@ __global__ void __launch_bounds__(CGRT_DEPOSIT_BLOCK, CGRT_DEPOSIT_MINB) photon_
         if (cand_total) atomicAdd(&ctr->candidates, cand_total);
         if (dep_total) atomicAdd(&ctr->deposits, dep_total);
         if (npair) atomicAdd(&ctr->exact_tests, (unsigned long long)npair);
+        if (ngroup) atomicAdd(&ctr->cell_groups, (unsigned long long)ngroup);
+        if (nstaged) atomicAdd(&ctr->staged_candidates, (unsigned long long)nstaged);
     }
 }
 

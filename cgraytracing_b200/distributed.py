@@ -48,16 +48,39 @@ class _DevArray:
         self.__cuda_array_interface__ = {"shape": (n,), "typestr": typestr, "data": (ptr, False), "version": 2}
 
 
-class GpuEngine:
-    """Adapter of a `Context` (C ABI) to the engine protocol; tensors are zero-copy views of ctx-owned device memory."""
+def make_native_comm(device: int, rank: int, world: int, group=None) -> int:
+    """An NCCL communicator owned by the C ABI side (cgrt_comm_init_rank): rank 0 makes the 128-byte id, torch.distributed only
+    carries it to the other ranks. -> ncclComm_t handle for Context.set_comm / allgather_hitpoints."""
+    import torch.distributed as dist
 
-    def __init__(self, ctx, device: int):
+    from .binding import comm_init_rank, comm_unique_id
+
+    box = [comm_unique_id() if rank == 0 else None]
+    dist.broadcast_object_list(box, src=0, group=group)
+    return comm_init_rank(device, rank, world, box[0])
+
+
+class GpuEngine:
+    """Adapter of a `Context` (C ABI) to the engine protocol; tensors are zero-copy views of ctx-owned device memory.
+
+    With `comm` (a handle from make_native_comm) both collectives of the path run INSIDE the library on its own streams
+    (cgrt_allgather_hitpoints; the all-reduce is part of cgrt_round_update and overlaps the next round's trace launches).
+    Without it the host framework reduces the accumulator buffer itself (torch.distributed on the library's stream)."""
+
+    def __init__(self, ctx, device: int, comm=None, world: int = 1):
         import torch
 
         self.ctx, self.device, self.torch = ctx, device, torch
+        self.comm, self.world = comm, world
+        self.native_collectives = comm is not None
+        if comm is not None:
+            ctx.set_comm(comm, world)
         # collectives are enqueued relative to the library's own stream: no host synchronisation between the photon pass, the
         # all-reduce and the update
         self.stream = torch.cuda.ExternalStream(ctx.stream(), device=torch.device("cuda", device))
+
+    def allgather_hitpoints(self):
+        self.ctx.allgather_hitpoints(self.comm, self.world)
 
     def collective_scope(self):
         return self.torch.cuda.stream(self.stream)
@@ -116,6 +139,10 @@ class ShardedRenderer:
             y0, y1 = row_shard(height, self.rank, self.world)
             if y1 > y0:
                 self.e.eye_pass(y0, y1)
+            if getattr(self.e, "native_collectives", False):
+                self.e.allgather_hitpoints()
+                self.e.build_grid()
+                return
             mine = self.e.export_hitpoints()
             counts = torch.zeros(self.world, dtype=torch.int64, device=mine.device)
             counts[self.rank] = mine.shape[0]
@@ -136,7 +163,7 @@ class ShardedRenderer:
         first, count = photon_shard(self.rounds_done, photons_per_round, self.rank, self.world)
         if count:
             self.e.photon_pass(first, count)
-        if self.world > 1:
+        if self.world > 1 and not getattr(self.e, "native_collectives", False):
             import torch.distributed as dist
 
             import contextlib

@@ -27,6 +27,7 @@
 #include <sstream>
 #include <stdexcept>
 #include <string>
+#include <thread>
 #include <vector>
 
 #include "cgrt.h"
@@ -291,6 +292,9 @@ struct RenderOptions {
     int accum_mode = 0;                  // 0: fp64 atomics, 1: float32 x4 accumulators
     uint64_t seed = 20261018ull;
     int device = 0;
+    int num_gpus = 1;                    // > 1: devices device .. device+num_gpus-1 of this box, one context and one host thread per GPU:
+                                         // image rows and photon index ranges are split between them, NCCL (through the C ABI) carries the
+                                         // hitpoint records and the per-round accumulators
 };
 
 struct Image {
@@ -300,8 +304,10 @@ struct Image {
     Vec3 at(int h, int w) const { const double *p = &rgb[((size_t)h * width + w) * 3]; return Vec3(p[0], p[1], p[2]); }
 };
 
-inline Image render(const std::vector<Object *> &objs, const RenderOptions &opt = RenderOptions(), cgrt_counters *counters = nullptr) {
-    Context c(opt.device);
+// One rank of render(): the whole of main.cpp:169-266 on one GPU for its share of the rows and of the photon indices. comm == nullptr:
+// the single-GPU render.
+inline Image render_rank(const std::vector<Object *> &objs, const RenderOptions &opt, int rank, int world, void *comm, cgrt_counters *counters) {
+    Context c(opt.device + rank);
     cgrt_config cfg;
     cgrt_default_config(&cfg);
     cfg.width = opt.width; cfg.height = opt.height; cfg.num_of_samples = opt.num_of_samples; cfg.use_dof = opt.depth_of_field ? 1 : 0;
@@ -309,14 +315,24 @@ inline Image render(const std::vector<Object *> &objs, const RenderOptions &opt 
     c.check(cgrt_set_config(c.get(), &cfg));
     for (const Object *o : objs) o->describe(c);  // object id = position in objs, like the reference's loop index (main.cpp:55)
     c.check(cgrt_commit_scene(c.get()));
-    c.check(cgrt_eye_pass(c.get(), 0, opt.height));   // main.cpp:185-219
+    // main.cpp:185-219: contiguous row tiles, the remainder to the low ranks
+    const int base = opt.height / world, rem = opt.height % world;
+    const int y0 = rank * base + (rank < rem ? rank : rem), y1 = y0 + base + (rank < rem ? 1 : 0);
+    if (y1 > y0) c.check(cgrt_eye_pass(c.get(), y0, y1));
+    if (comm) {
+        c.check(cgrt_allgather_hitpoints(c.get(), comm, world));
+        c.check(cgrt_set_comm(c.get(), comm, world));  // cgrt_round_update all-reduces the accumulators from now on
+    }
     c.check(cgrt_build_grid(c.get()));                // hash.h:43-54 as a sorted grid
     const uint64_t total = (uint64_t)opt.num_photon * (uint64_t)opt.num_threads;
     const int rounds = opt.rounds < 1 ? 1 : opt.rounds;
     uint64_t done = 0;
     for (int r = 0; r < rounds; r++) {                // main.cpp:221-249
-        uint64_t n = total / rounds + ((uint64_t)r < total % rounds ? 1 : 0);
-        c.check(cgrt_photon_pass(c.get(), done, n));
+        const uint64_t n = total / rounds + ((uint64_t)r < total % rounds ? 1 : 0);
+        const uint64_t pb = n / world, pr = n % world;  // this rank's index range of the round
+        const uint64_t first = done + (uint64_t)rank * pb + ((uint64_t)rank < pr ? (uint64_t)rank : pr);
+        const uint64_t mine = pb + ((uint64_t)rank < pr ? 1 : 0);
+        if (mine) c.check(cgrt_photon_pass(c.get(), first, mine));
         c.check(cgrt_round_update(c.get()));
         done += n;
     }
@@ -326,7 +342,42 @@ inline Image render(const std::vector<Object *> &objs, const RenderOptions &opt 
     img.rgb8.resize(img.rgb.size());
     c.check(cgrt_gather_image(c.get(), (double)total, img.rgb.data(), img.rgb8.data()));  // main.cpp:252-258 (the library applies num_of_samples), 403-411
     if (counters) c.check(cgrt_get_counters(c.get(), counters));
+    if (comm) c.check(cgrt_set_comm(c.get(), nullptr, 1));
     return img;
+}
+
+inline Image render(const std::vector<Object *> &objs, const RenderOptions &opt = RenderOptions(), cgrt_counters *counters = nullptr) {
+    const int world = opt.num_gpus < 1 ? 1 : opt.num_gpus;
+    if (world == 1) return render_rank(objs, opt, 0, 1, nullptr, counters);
+    std::vector<int> devs((size_t)world);
+    for (int k = 0; k < world; k++) devs[(size_t)k] = opt.device + k;
+    std::vector<void *> comms((size_t)world, nullptr);
+    int rc = cgrt_comm_init_all(world, devs.data(), comms.data());
+    if (rc != 0) throw Error(rc, "cgrt_comm_init_all failed (NCCL missing, or fewer GPUs than num_gpus?)");
+    std::vector<Image> imgs((size_t)world);
+    std::vector<cgrt_counters> ctrs((size_t)world);
+    std::vector<std::string> errs((size_t)world);
+    std::vector<int> stat((size_t)world, 0);
+    std::vector<std::thread> th;
+    for (int k = 0; k < world; k++)
+        th.emplace_back([&, k] {
+            try { imgs[(size_t)k] = render_rank(objs, opt, k, world, comms[(size_t)k], &ctrs[(size_t)k]); }
+            catch (const Error &e) { stat[(size_t)k] = e.status ? e.status : CGRT_ERR_CUDA; errs[(size_t)k] = e.what(); }
+        });
+    for (auto &t : th) t.join();
+    for (void *cm : comms) cgrt_comm_destroy(cm);
+    for (int k = 0; k < world; k++)
+        if (stat[(size_t)k]) throw Error(stat[(size_t)k], "rank " + std::to_string(k) + ": " + errs[(size_t)k]);
+    if (counters) {  // the job's totals: per-rank work counters add up, the hitpoint set is replicated
+        *counters = ctrs[0];
+        for (int k = 1; k < world; k++) {
+            counters->eye_segments += ctrs[(size_t)k].eye_segments; counters->photon_segments += ctrs[(size_t)k].photon_segments;
+            counters->diffuse_hits += ctrs[(size_t)k].diffuse_hits; counters->candidates += ctrs[(size_t)k].candidates;
+            counters->deposits += ctrs[(size_t)k].deposits; counters->gathered_hits += ctrs[(size_t)k].gathered_hits;
+            counters->exact_tests += ctrs[(size_t)k].exact_tests; counters->gpu_launches += ctrs[(size_t)k].gpu_launches;
+        }
+    }
+    return imgs[0];  // every rank holds the same picture
 }
 
 // ---------------------------------------------------------------------------------------------------------------------

@@ -57,6 +57,8 @@ typedef struct cgrt_counters {
     uint64_t gpu_launches;                  /* kernels launched by this ctx so far */
     uint64_t gathered_hits;                 /* diffuse hits that went through the 27-cell gather (= diffuse_hits unless culling is on) */
     uint64_t exact_tests;                   /* (hit, hitpoint) pairs that passed the fp32 prefilter and took the fp64 test of main.cpp:116 */
+    uint64_t cell_groups;                   /* deposit kernel: groups of hits in one cell that shared one reading of the 27 bucket lists */
+    uint64_t staged_candidates;             /* bucket entries read for those groups (each once per group, not once per hit) */
 } cgrt_counters;
 
 /* ---- lifecycle ------------------------------------------------------------------------------------------------ */
@@ -126,7 +128,23 @@ int cgrt_build_grid(cgrt_ctx *ctx);
 int cgrt_photon_pass(cgrt_ctx *ctx, uint64_t first, uint64_t count);
 /* Device view of the per-round accumulators {dflux[3], m} (4 x fp64 per hitpoint, canonical order) for the all-reduce. */
 int cgrt_accum_dev(cgrt_ctx *ctx, void **ptr_dev, int64_t *n_doubles);
-/* All-reduce the accumulators over an NCCL communicator (ncclComm_t as void*; NULL: single GPU, no-op). */
+/* ---- multi-GPU: NCCL is bound at run time (the copy already loaded in the process, else libnccl.so.2); none of
+ * these is needed on one GPU. A communicator is an ncclComm_t passed as void*. ------------------------------------------------ */
+/* Communicators without nccl.h on the host side: a 128-byte ncclUniqueId made on rank 0 and carried to the others by whatever the
+ * launcher offers (one process per GPU), or all devices of one process at once (one thread per ctx). */
+int cgrt_comm_unique_id(void *id128);
+int cgrt_comm_init_rank(int device, int rank, int world, const void *id128, void **comm);
+int cgrt_comm_init_all(int n, const int *devices /* NULL: 0..n-1 */, void **comms /* n */);
+int cgrt_comm_destroy(void *comm);
+/* Tile-sharded eye pass: all-gather the hitpoint records of every rank's rows (after cgrt_eye_pass(y0,y1), before cgrt_build_grid);
+ * every rank then builds the same grid from the union. */
+int cgrt_allgather_hitpoints(cgrt_ctx *ctx, void *nccl_comm, int world);
+/* Attach a communicator: from now on cgrt_round_update all-reduces the accumulators {dflux.xyz, m} over it before applying the update.
+ * The all-reduce and the update run on a side stream of the ctx and are only waited for by the NEXT round's gather, so the next round's
+ * emission and traversal launches run underneath the collective. NULL detaches. */
+int cgrt_set_comm(cgrt_ctx *ctx, void *nccl_comm, int world);
+/* All-reduce the accumulators now, on the ctx stream, asynchronously (NULL: single GPU, no-op). For hosts that drive the collective
+ * themselves; with cgrt_set_comm it is implied by cgrt_round_update. */
 int cgrt_allreduce_accum(cgrt_ctx *ctx, void *nccl_comm);
 /* Per-round radius/flux update (main.cpp:119-122 in its batched form, SURVEY Q1 "U2"), then clears the accumulators. */
 int cgrt_round_update(cgrt_ctx *ctx);
@@ -174,6 +192,8 @@ int cgrt_get_timings(cgrt_ctx *ctx, double ms[12]);
  * environment every device buffer of a context sits between two 4 KiB fences of a known byte pattern. Synchronises and returns in
  * *damaged the number of fence bytes kernels have overwritten so far (released buffers included); 0 when the mode is off. */
 int cgrt_check_guards(cgrt_ctx *ctx, uint64_t *damaged);
+/* Photons one trace launch of cgrt_photon_pass takes (sized from free device memory at the first pass; 0 before it). */
+int cgrt_photon_chunk(cgrt_ctx *ctx, uint64_t *photons_per_launch);
 /* The library keeps the large device buffers of destroyed contexts (deposit tables, photon queues, ray queues) parked per device and
  * hands them to the next context: a render() creates and destroys one. Parked blocks are released automatically when an allocation
  * would otherwise fail; this call releases them now (device < 0: all devices). bytes_released may be NULL. */

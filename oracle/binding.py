@@ -510,3 +510,12 @@ class Ref:
 
     def image_size(self):
         return self.L.ref_image_width(), self.L.ref_image_height()
+
+    def eye_pass_as_shipped(self):
+        """main.cpp:185-219 over the compiled-in image through the reference's own trace()."""
+        self.L.ref_eye_pass_as_shipped()
+
+    def photon_loop_as_shipped(self, num_photon, num_threads=8, seed=1):
+        """main.cpp:222-249: every one of `num_threads` threads traces `num_photon` photons (glibc rand() and its lock). -> seconds"""
+        self.L.ref_photon_loop_as_shipped.restype = C.c_double
+        return float(self.L.ref_photon_loop_as_shipped(int(num_photon), int(num_threads), C.c_uint(seed)))

@@ -280,6 +280,51 @@ int ref_gather_image(double n_emitted, int W, int H, double *rgb) {
     return 0;
 }
 
+// ---- "reference as shipped": the two loops of render() (main.cpp:185-219, 222-249) around the reference's own trace(), objects,
+// samplers and Hashtable. render() itself cannot be called for a benchmark: its photon count (2,560,000 x 8 threads, ~8 minutes) and its
+// output buffer are literals. The loops below keep its structure statement for statement — including the nested `omp parallel for`
+// that makes EVERY thread trace num_photon photons (main.cpp:222), the per-thread srand(), glibc's rand() (one global lock shared by all
+// threads: where most of the shipped binary's time goes) and the unsynchronised updates of the shared table.
+int ref_eye_pass_as_shipped() {
+    const Vec3 camorg = Vec3(0, 0, -10);
+    delete g.ht;
+    g.ht = new Hashtable(1000001, 200.0 / height);  // main.cpp:183-184
+    g_use_stream = true;                            // the eye pass only draws the unused lens sample (main.cpp:205): keep it deterministic
+    for (int h = 0; h < height; h++)
+        for (int w = 0; w < width; w++) {
+            double x = (2.0 * ((double)w / width) - 1) * 10.0;
+            double y = (2.0 * ((double)h / height) - 1) * 10.0 * height / width;
+            Vec3 dir = (Vec3(x, y, 0) - camorg).normalize();
+            Vec3 neworg = camorg + uniform_sampling_circle(1.5);  // main.cpp:205, result unused
+            (void)neworg;
+            trace(camorg, dir, g.objs, Vec3(), Vec3(1, 1, 1), true, 0, *g.ht, w, h);  // main.cpp:209
+        }
+    return 0;
+}
+double ref_photon_loop_as_shipped(int num_photon, int num_threads, unsigned seed) {
+    if (!g.ht) return -1.0;
+    const Vec3 lightorg = Vec3(0, 19.999, 20);
+    Hashtable &htable = *g.ht;
+    g_use_stream = false;  // cgref_rand() -> glibc rand(), as shipped
+    double t0 = omp_get_wtime();
+    omp_set_num_threads(num_threads);
+#pragma omp parallel
+    {
+        srand((int)seed ^ omp_get_thread_num());  // main.cpp:229 (time(NULL) -> seed)
+#pragma omp parallel for
+        for (int i = 0; i < num_photon; i++) {
+            double a = uniform_sampling_zeroone() * 4 - 2;
+            double b = uniform_sampling_zeroone() * 4 - 2;
+            Vec3 disturbance = Vec3(a, 0, b);
+            Vec3 dir = uniform_sampling_sphere();
+            trace(lightorg + disturbance, dir, g.objs, Vec3(700, 700, 700) * (PI * 4.0), Vec3(1, 1, 1), false, 0, htable, 0, 0);
+        }
+    }
+    double sec = omp_get_wtime() - t0;
+    g_use_stream = true;
+    return sec;
+}
+
 // The reference's texture decoder (vendored stb_image v2.19, main.cpp:300). Returns malloc'd RGB8; free with ref_free.
 uint8_t *ref_stbi_load(const char *path, int *w, int *h) {
     int bpp;

@@ -77,3 +77,23 @@ def test_cpp_render_equals_python_binding(host_bins, gpu, tmp_path, scene, prese
     # fp64 atomics commute only up to rounding: the 8-bit pictures agree except for rare +-1 levels
     assert np.abs(got8.astype(int) - rgb8.astype(int)).max() <= 1
     assert abs(float(out[3]) - rgb8.mean()) < 0.01
+
+
+@pytest.mark.gpu
+def test_cpp_two_gpu_render_equals_one_gpu(host_bins, tmp_path):
+    """render() with num_gpus = 2 (one host thread and one context per GPU; rows and photon ranges split; hitpoint records all-gathered and
+    accumulators all-reduced by NCCL behind the C ABI) == the one-GPU render: same hitpoints, same deposits, same picture."""
+    import torch
+
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs two GPUs on one box (gpurun --gpus 2)")
+    exe, _ = host_bins
+    assets = os.path.join(ROOT, "cgraytracing_b200", "assets")
+    outs = []
+    for gpus in (1, 2):
+        o = subprocess.check_output([exe, "bunny", "160", "120", "60001", "3", str(tmp_path / f"o{gpus}.ppm"), assets, str(gpus)], text=True).split()
+        outs.append(o)
+    assert outs[0][0] == outs[1][0] and outs[0][1] == outs[1][1] and int(outs[0][1]) > 0   # hitpoints, deposits
+    a, b = (np.frombuffer((tmp_path / f"o{g}.ppm").read_bytes()[-160 * 120 * 3:], np.uint8) for g in (1, 2))
+    assert np.abs(a.astype(int) - b.astype(int)).max() <= 1   # fp64 atomics + all-reduce order: identical up to rare +-1 levels
+    assert abs(float(outs[0][3]) - float(outs[1][3])) < 0.01
