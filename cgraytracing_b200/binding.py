@@ -27,7 +27,7 @@ ABI_SYMBOLS = [
     "cgrt_count_traversal", "cgrt_eye_pass", "cgrt_export_hitpoints_dev", "cgrt_import_hitpoints_dev", "cgrt_build_grid", "cgrt_photon_pass",
     "cgrt_accum_dev", "cgrt_allreduce_accum", "cgrt_round_update", "cgrt_gather_image", "cgrt_num_hitpoints", "cgrt_download_hitpoints",
     "cgrt_download_accum", "cgrt_download_grid", "cgrt_get_counters", "cgrt_get_timings", "cgrt_set_counting", "cgrt_set_profiling", "cgrt_set_culling", "cgrt_set_overlap", "cgrt_average_u8", "cgrt_average_f64",
-    "cgrt_check_guards", "cgrt_release_cached_memory", "cgrt_photon_chunk",
+    "cgrt_check_guards", "cgrt_release_cached_memory", "cgrt_photon_chunk", "cgrt_deposit_record_bytes",
     "cgrt_comm_unique_id", "cgrt_comm_init_rank", "cgrt_comm_init_all", "cgrt_comm_destroy", "cgrt_allgather_hitpoints", "cgrt_set_comm",
 ]
 

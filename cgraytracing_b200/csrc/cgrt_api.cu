@@ -1708,6 +1708,8 @@ int cgrt_release_cached_memory(int device, uint64_t *bytes_released) {
     return CGRT_OK;
 }
 
+int cgrt_deposit_record_bytes(void) { return (int)sizeof(DepositRec); }
+
 int cgrt_photon_chunk(cgrt_ctx *ctx, uint64_t *photons_per_launch) {
     if (!ctx || !photons_per_launch) return CGRT_ERR_INVALID;
     *photons_per_launch = (uint64_t)(ctx->photon_chunk ? ctx->photon_chunk : ctx->auto_chunk);
