@@ -470,14 +470,12 @@ int build_bvh(cgrt_ctx *ctx, double *tri9_dev, int n, double orient_sign, int sl
     TriRec *tris;
     int *tri_id;
     float *box;
-    BvhNode *nodes;
     int *left, *right, *parent;
     unsigned int *flags;
     int ninternal = n > 1 ? n - 1 : 0;
     CKS(dalloc(ctx, &tris, (size_t)n));
     CKS(dalloc(ctx, &tri_id, (size_t)n));
     CKS(dalloc(ctx, &box, (size_t)(2 * n) * 6));
-    CKS(dalloc(ctx, &nodes, (size_t)(ninternal > 0 ? ninternal : 1)));
     CKS(dalloc(ctx, &left, (size_t)n));
     CKS(dalloc(ctx, &right, (size_t)n));
     CKS(dalloc(ctx, &parent, (size_t)(2 * n)));
@@ -489,9 +487,32 @@ int build_bvh(cgrt_ctx *ctx, double *tri9_dev, int n, double orient_sign, int sl
     if (ninternal > 0) {
         lbvh_hierarchy_kernel<<<nblk(ninternal, T), T, 0, ctx->stream>>>(keys_sorted, n, left, right, parent);
         lbvh_refit_kernel<<<nblk(n, T), T, 0, ctx->stream>>>(n, left, right, parent, box, flags);
-        lbvh_pack_kernel<<<nblk(ninternal, T), T, 0, ctx->stream>>>(n, left, right, box, nodes);
-        ctx->launches += 3;
+        ctx->launches += 2;
     }
+    // ---- 4-wide nodes: collapse level by level (the host only reads one counter per level)
+    BvhNode4 *nodes4;
+    int *wqueue, *wcounter;
+    CKS(dalloc(ctx, &nodes4, (size_t)(ninternal > 0 ? ninternal : 1)));
+    CKS(dalloc(ctx, &wqueue, (size_t)(ninternal > 0 ? ninternal : 1)));
+    CKS(dalloc(ctx, &wcounter, 1));
+    int wide_levels = 0;
+    if (ninternal > 0) {
+        int one = 1, zero = 0;
+        CK(cudaMemcpyAsync(wqueue, &zero, sizeof zero, cudaMemcpyHostToDevice, ctx->stream));  // wide node 0 = binary root 0
+        CK(cudaMemcpyAsync(wcounter, &one, sizeof one, cudaMemcpyHostToDevice, ctx->stream));
+        int begin = 0, end = 1;
+        while (begin < end) {
+            lbvh_collapse_kernel<<<nblk(end - begin, T), T, 0, ctx->stream>>>(n, begin, end, left, right, box, wqueue, wcounter, nodes4);
+            ctx->launches++;
+            int total = 0;
+            CK(cudaMemcpyAsync(&total, wcounter, sizeof total, cudaMemcpyDeviceToHost, ctx->stream));
+            CK(cudaStreamSynchronize(ctx->stream));
+            begin = end; end = total;
+            wide_levels++;
+        }
+    }
+    // traversal stack: at most three pushes per wide level (CGRT_BVH_STACK entries)
+    if (3 * wide_levels + 4 > CGRT_BVH_STACK) FAIL(CGRT_ERR_CAPACITY, "mesh hierarchy too deep for the traversal stack");
     float root[6];  // box 0 is the root (the only leaf when n == 1)
     CK(cudaMemcpyAsync(root, box, sizeof root, cudaMemcpyDeviceToHost, ctx->stream));
     CK(cudaStreamSynchronize(ctx->stream));
@@ -501,10 +522,11 @@ int build_bvh(cgrt_ctx *ctx, double *tri9_dev, int n, double orient_sign, int sl
         B.root_lo[a] = root[a]; B.root_hi[a] = root[3 + a];
         if (!(std::fabs(root[a]) <= CGRT_F32_BOUND && std::fabs(root[3 + a]) <= CGRT_F32_BOUND)) B.f32_ok = 0;
     }
-    B.nodes = nodes;
+    B.nodes4 = nodes4;
     B.tris = tris;
     B.tri_id = tri_id;
     CKS(dfree(ctx, bounds)); CKS(dfree(ctx, keys)); CKS(dfree(ctx, keys_sorted)); CKS(dfree(ctx, perm));
+    CKS(dfree(ctx, wqueue)); CKS(dfree(ctx, wcounter));
     CKS(dfree(ctx, box)); CKS(dfree(ctx, left)); CKS(dfree(ctx, right)); CKS(dfree(ctx, parent)); CKS(dfree(ctx, flags));
     return 0;
 }

@@ -1,5 +1,5 @@
 // cgrt_build.cuh — hand-written device builders: LSD radix sort (keys + permutation), LBVH (Morton codes ->
-// sort -> Karras hierarchy -> bottom-up refit -> 64-byte two-box nodes), and the displaced height-field mesh.
+// sort -> Karras hierarchy -> bottom-up refit -> top-down collapse into 128-byte four-box nodes), and the displaced height-field mesh.
 // Replaces std::sort / KDTree::buildKdTree (objects.h:217-267), Plane's bump ctor (objects.h:482-503) and
 // Hashtable::insert's bucket vectors (hash.h:43-54).
 #pragma once
@@ -249,20 +249,62 @@ __global__ void lbvh_refit_kernel(int n, const int *__restrict__ left, const int
     }
 }
 
-__global__ void lbvh_pack_kernel(int n, const int *__restrict__ left, const int *__restrict__ right, const float *__restrict__ box, BvhNode *__restrict__ nodes) {
-    int i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= n - 1) return;
-    int l = left[i], r = right[i];
-    BvhNode N;
-    const float *a = box + (size_t)l * 6, *b = box + (size_t)r * 6;
-    for (int c = 0; c < 3; c++) {
-        N.lo0[c] = a[c]; N.hi0[c] = a[3 + c];
-        N.lo1[c] = b[c]; N.hi1[c] = b[3 + c];
+// Top-down collapse of the binary hierarchy into 4-wide nodes, one level per launch. wide node w in [begin, end) stands for the binary
+// internal node queue[w]; its children are that node's two children, the one with the largest box area being replaced by its own two
+// children until there are four (or no internal child is left). Internal children get the next free wide indices (atomic counter; the
+// memory position of a node does not influence any result: slots inside a node are ordered by binary box id, which is deterministic).
+__device__ __forceinline__ float lbvh_box_area(const float *__restrict__ b) {
+    const float dx = b[3] - b[0], dy = b[4] - b[1], dz = b[5] - b[2];
+    return dx * dy + dy * dz + dz * dx;
+}
+__global__ void lbvh_collapse_kernel(int n, int begin, int end, const int *__restrict__ left, const int *__restrict__ right, const float *__restrict__ box,
+                                     int *__restrict__ queue, int *__restrict__ counter, BvhNode4 *__restrict__ nodes4) {
+    int w = begin + blockIdx.x * blockDim.x + threadIdx.x;
+    if (w >= end) return;
+    const int b = queue[w];
+    int c[4];
+    int nc = 2;
+    c[0] = left[b]; c[1] = right[b]; c[2] = -1; c[3] = -1;
+    while (nc < 4) {
+        int pick = -1;
+        float best = -1.f;
+        for (int j = 0; j < nc; j++) {
+            if (c[j] >= n - 1) continue;  // a leaf
+            float a = lbvh_box_area(box + (size_t)c[j] * 6);
+            if (a > best) { best = a; pick = j; }
+        }
+        if (pick < 0) break;
+        const int e = c[pick];
+        c[pick] = left[e];
+        c[nc++] = right[e];
     }
-    N.c0 = (l >= n - 1) ? ~(l - (n - 1)) : l;
-    N.c1 = (r >= n - 1) ? ~(r - (n - 1)) : r;
-    N.pad0 = 0; N.pad1 = 0;
-    nodes[i] = N;
+    // slots in ascending box id (insertion sort of <= 4 entries)
+    for (int i = 1; i < nc; i++) {
+        int v = c[i], j = i - 1;
+        while (j >= 0 && c[j] > v) { c[j + 1] = c[j]; j--; }
+        c[j + 1] = v;
+    }
+    BvhNode4 N;
+    for (int j = 0; j < 4; j++) {
+        if (j < nc) {
+            const float *bb = box + (size_t)c[j] * 6;
+            N.lox[j] = bb[0]; N.loy[j] = bb[1]; N.loz[j] = bb[2];
+            N.hix[j] = bb[3]; N.hiy[j] = bb[4]; N.hiz[j] = bb[5];
+            if (c[j] >= n - 1) {
+                N.child[j] = ~(c[j] - (n - 1));
+            } else {
+                const int at = atomicAdd(counter, 1);
+                queue[at] = c[j];
+                N.child[j] = at;
+            }
+        } else {
+            N.lox[j] = N.loy[j] = N.loz[j] = 3.0e38f;
+            N.hix[j] = N.hiy[j] = N.hiz[j] = -3.0e38f;
+            N.child[j] = CGRT_NO_CHILD;
+        }
+        N.pad[j] = 0;
+    }
+    nodes4[w] = N;
 }
 
 // =================================================================================================================

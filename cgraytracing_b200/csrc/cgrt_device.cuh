@@ -158,13 +158,14 @@ enum { MAT_DIFFUSE = 0, MAT_MIRROR = 1, MAT_GLASS = 2 };  // main.cpp:82,129,135
 #define CGRT_MAX_BEZIER 2
 #define CGRT_MAX_CP 7
 
-// One BVH2 node, 64 bytes = two 32-byte sectors: both children's boxes (float, rounded outward + padded) and links.
-// child >= 0: internal node index; child < 0: leaf, ~child = index into the Morton-sorted triangle array.
-struct __align__(16) BvhNode {
-    float lo0[3], hi0[3];
-    float lo1[3], hi1[3];
-    int c0, c1;
-    int pad0, pad1;
+// One 4-wide node, 128 bytes = one cache line: the (float, padded) boxes of up to four children, component by component, and their links.
+// child >= 0: 4-wide node index; child < 0: leaf, ~child = index into the Morton-sorted triangle array; CGRT_NO_CHILD: empty slot.
+// Built by collapsing the binary LBVH top down (lbvh_collapse_kernel): a traversal reads half as many dependent nodes per ray.
+#define CGRT_NO_CHILD ((int)0x80000000)
+struct __align__(16) BvhNode4 {
+    float lox[4], loy[4], loz[4], hix[4], hiy[4], hiz[4];
+    int child[4];
+    int pad[4];
 };
 // One triangle, 96 bytes = three sectors: pa and the edges / normal exactly as Triangle::intersect forms them
 // (objects.h:98-99,107): e1 = pa - pb, e2 = pa - pc, n = normalize(e1 x e2).
@@ -181,7 +182,7 @@ struct ObjDev {
     double refl, transp;
 };
 struct BvhDev {
-    const BvhNode *nodes;
+    const BvhNode4 *nodes4;
     const TriRec *tris;
     const int *tri_id;      // sorted position -> original triangle index
     int ntris;
@@ -240,32 +241,6 @@ __device__ __forceinline__ bool tri_intersect(const TriRec *T, d3 o, d3 d, doubl
     d3 e1 = mk(a1.y, a2.x, a2.y);
     d3 e2 = mk(a3.x, a3.y, a4);
     d3 s = pa - o;
-#ifdef CGRT_TRI_PRETEST
-    // (Off: correct — all GPU parity tests pass with it — but measured slower inside the 64-register traversal kernel, 5.73 vs 5.15 ms per
-    // round: the twelve conversions and the extra live floats cost more than the skipped fp64 determinants save at 1.7 live lanes.)
-    {   // Conservative float reject: about four of five triangles a traversal reaches are missed, and 99 % of those misses are decided by
-        // the signs of three float determinants (tools/tri_pretest_study.py: 0 false rejects). A float determinant of float-rounded
-        // inputs is off by <= 10 u * (sum of its |products|) <= 60 u |a| |b| |c| (infinity norms, u = 2^-24); 96 u is used, plus 1e-30
-        // so that nothing is decided in the denormal range. Only a certain sign of det1 and a certain violation of u >= 0, v >= 0 or
-        // u + v <= 1 rejects; everything else takes the reference's fp64 test below.
-        const float dx = (float)d.x, dy = (float)d.y, dz = (float)d.z;
-        const float ax = (float)e1.x, ay = (float)e1.y, az = (float)e1.z;
-        const float bx = (float)e2.x, by = (float)e2.y, bz = (float)e2.z;
-        const float sx = (float)s.x, sy = (float)s.y, sz = (float)s.z;
-        // det3(a, b, c) = a.x b.y c.z + b.x c.y a.z + c.x a.y b.z - a.x c.y b.z - b.x a.y c.z - c.x b.y a.z
-        const float f1 = dx * ay * bz + ax * by * dz + bx * dy * az - dx * by * az - ax * dy * bz - bx * ay * dz;  // (d, e1, e2)
-        const float f3 = dx * sy * bz + sx * by * dz + bx * dy * sz - dx * by * sz - sx * dy * bz - bx * sy * dz;  // (d, s, e2)
-        const float f4 = dx * ay * sz + ax * sy * dz + sx * dy * az - dx * sy * az - ax * dy * sz - sx * ay * dz;  // (d, e1, s)
-        const float nd = fmaxf(fmaxf(fabsf(dx), fabsf(dy)), fabsf(dz)), na = fmaxf(fmaxf(fabsf(ax), fabsf(ay)), fabsf(az));
-        const float nb = fmaxf(fmaxf(fabsf(bx), fabsf(by)), fabsf(bz)), ns = fmaxf(fmaxf(fabsf(sx), fabsf(sy)), fabsf(sz));
-        const float K = 96.0f * 5.9604645e-8f;
-        const float c1 = K * nd * na * nb + 1e-30f, c3 = K * nd * ns * nb + 1e-30f, c4 = K * nd * na * ns + 1e-30f;
-        if (fabsf(f1) > c1) {
-            const float sg = f1 > 0.f ? 1.f : -1.f;
-            if (f3 * sg < -c3 || f4 * sg < -c4 || (f3 + f4 - f1) * sg > c1 + c3 + c4) return false;
-        }
-    }
-#endif
     double det1 = det3(d, e1, e2);
     if (det1 == 0.0 || det1 != det1) return false;  // x/0 -> inf/nan never satisfies all four tests
     double det3v = det3(d, s, e2);
@@ -360,119 +335,116 @@ __device__ __forceinline__ bool root_box_hit(const BvhDev &B, d3 o, d3 d, double
     return tn <= tf;
 }
 
-// (A "while-while" ordering that parks lanes on their leaf until the warp reconverges was measured slower here: 8.8 ms
-// vs 7.0 ms per 16 Mi-photon round for the traversal launches, 5.3 vs 7.5 live lanes per instruction.)
-template <bool COUNT>
-__device__ __forceinline__ bool bvh_closest(const BvhDev &B, d3 o, d3 d, double tmax, double &t_out, int &leaf_out, TravCounters *tc) {
-    SlabRay R = make_slab_ray(o, d, B.f32_ok != 0);
-    double best = tmax;
-    float best_up = __double2float_ru(tmax);
-    int best_leaf = -1;
-    int stack[64];
-    int sp = 0;
-    int node = B.root_is_leaf ? ~0 : 0;
-    for (;;) {
-        if (node >= 0) {
-            // 64 bytes as four 16-byte loads
-            const float4 *q = reinterpret_cast<const float4 *>(B.nodes + node);
-            float4 q0 = __ldg(q), q1 = __ldg(q + 1), q2 = __ldg(q + 2), q3 = __ldg(q + 3);
-            if (COUNT) tc->node_visits++;
-            int c0 = __float_as_int(q3.x), c1 = __float_as_int(q3.y);
-            float tn0, tn1;
-            bool h0 = slab_any(q0.x, q0.y, q0.z, q0.w, q1.x, q1.y, R, best, best_up, tn0);
-            bool h1 = slab_any(q1.z, q1.w, q2.x, q2.y, q2.z, q2.w, R, best, best_up, tn1);
-            if (h0 && h1) {
-                if (tn1 < tn0) { int tmp = c0; c0 = c1; c1 = tmp; }
-                stack[sp++] = c1;
-                node = c0;
-            } else if (h0) {
-                node = c0;
-            } else if (h1) {
-                node = c1;
-            } else {
-                if (sp == 0) break;
-                node = stack[--sp];
-            }
-        } else {
-            int leaf = ~node;
-            if (COUNT) tc->tri_tests++;
-            double t;
-            if (tri_intersect(B.tris + leaf, o, d, t) && t < best) {
-                best = t;
-                best_up = __double2float_ru(t);
-                best_leaf = leaf;
-            }
-            if (sp == 0) break;
-            node = stack[--sp];
-        }
-    }
-    t_out = best;
-    leaf_out = best_leaf;
-    return best_leaf >= 0;
+// ---------------------------------------------------------------------------------------------------------------
+// Closest-hit search over the 4-wide nodes. One node visit = one 128-byte line = four box tests;
+// the children that are hit are entered nearest first (sorting network over four 32-bit keys: entry distance with the slot number in the
+// two lowest mantissa bits) and the others pushed farthest first (predicated stores: three unconditional stack stores per visit were
+// measured 11 % slower, the traversal is sensitive to every extra L1 transaction). F32ONLY: the instantiation for trees that lie within
+// CGRT_F32_BOUND (every mesh of the BASELINE scenes), without any fp64 box arithmetic: a ray that starts farther out than the bound is
+// re-based for the box tests only — its entry distance t0 into the padded root box is taken in fp64 once, the float slabs then run
+// from o + d t0 (on the root box, inside the bound) against best - t0; the triangle test keeps the original origin and the reference's
+// fp64 arithmetic. Otherwise SlabRay picks per ray.
+// (Measured and rejected on the 2-wide tree that preceded this one: a "while-while" ordering that parks lanes on their leaf until the
+// warp reconverges, 8.8 vs 7.0 ms; postponing the fp64 triangle tests to after the loop behind a conservative float classification of
+// every leaf, 5.21 vs 5.14 ms; L1 prefetch of the pushed children, 5.03 vs 4.89 ms. The 2-wide tree itself: 5.09 vs 4.61 ms.)
+// ---------------------------------------------------------------------------------------------------------------
+#ifndef CGRT_BVH_STACK
+#define CGRT_BVH_STACK 160   /* three pushes per wide level; cgrt_commit_scene refuses a deeper tree */
+#endif
+__device__ __forceinline__ float f4c(const float4 &v, int j) { return j == 0 ? v.x : (j == 1 ? v.y : (j == 2 ? v.z : v.w)); }
+__device__ __forceinline__ void cswap(unsigned int &a, unsigned int &b) {
+    const unsigned int lo = min(a, b), hi = max(a, b);
+    a = lo; b = hi;
 }
 
-// The same traversal for trees that lie within CGRT_F32_BOUND (every mesh of the BASELINE scenes), without any fp64 box arithmetic:
-// a ray that starts farther out than the bound is re-based for the box tests only — its entry distance t0 into the padded root box is
-// taken in fp64 once, the float slab tests then run from o + d t0 (which lies on the root box, inside the bound) against best - t0.
-// The triangle test keeps the original origin and the reference's fp64 arithmetic. Without the fp64 slab path the kernel keeps six
-// doubles less alive per thread (photon_traverse_kernel is capped at 64 registers).
-template <bool COUNT>
-__device__ __forceinline__ bool bvh_closest_f32(const BvhDev &B, d3 o, d3 d, double tmax, double &t_out, int &leaf_out, TravCounters *tc) {
+template <bool COUNT, bool F32ONLY>
+__device__ __forceinline__ bool bvh4_closest(const BvhDev &B, d3 o, d3 d, double tmax, double &t_out, int &leaf_out, TravCounters *tc) {
     double t0 = 0.0;
-    d3 ob = o;
-    if (!(fabs(o.x) <= CGRT_F32_BOUND && fabs(o.y) <= CGRT_F32_BOUND && fabs(o.z) <= CGRT_F32_BOUND)) {
-        const double ix = 1.0 / d.x, iy = 1.0 / d.y, iz = 1.0 / d.z;
-        const double tx0 = ((double)B.root_lo[0] - o.x) * ix, tx1 = ((double)B.root_hi[0] - o.x) * ix;
-        const double ty0 = ((double)B.root_lo[1] - o.y) * iy, ty1 = ((double)B.root_hi[1] - o.y) * iy;
-        const double tz0 = ((double)B.root_lo[2] - o.z) * iz, tz1 = ((double)B.root_hi[2] - o.z) * iz;
-        const double tn = fmax(fmax(fmin(tx0, tx1), fmin(ty0, ty1)), fmax(fmin(tz0, tz1), 0.0));
-        const double tf = fmin(fmin(fmax(tx0, tx1), fmax(ty0, ty1)), fmin(fmax(tz0, tz1), tmax));
-        if (!(tn <= tf)) { t_out = tmax; leaf_out = -1; return false; }  // misses the root box
-        t0 = tn * (1.0 - 1e-12);  // never beyond the true entry
-        ob = o + d * t0;
+    SlabRay R;
+    float ox, oy, oz, ix, iy, iz;
+    if (F32ONLY) {
+        d3 ob = o;
+        if (!(fabs(o.x) <= CGRT_F32_BOUND && fabs(o.y) <= CGRT_F32_BOUND && fabs(o.z) <= CGRT_F32_BOUND)) {
+            const double jx = 1.0 / d.x, jy = 1.0 / d.y, jz = 1.0 / d.z;
+            const double tx0 = ((double)B.root_lo[0] - o.x) * jx, tx1 = ((double)B.root_hi[0] - o.x) * jx;
+            const double ty0 = ((double)B.root_lo[1] - o.y) * jy, ty1 = ((double)B.root_hi[1] - o.y) * jy;
+            const double tz0 = ((double)B.root_lo[2] - o.z) * jz, tz1 = ((double)B.root_hi[2] - o.z) * jz;
+            const double tn = fmax(fmax(fmin(tx0, tx1), fmin(ty0, ty1)), fmax(fmin(tz0, tz1), 0.0));
+            const double tf = fmin(fmin(fmax(tx0, tx1), fmax(ty0, ty1)), fmin(fmax(tz0, tz1), tmax));
+            if (!(tn <= tf)) { t_out = tmax; leaf_out = -1; return false; }  // misses the root box
+            t0 = tn * (1.0 - 1e-12);  // never beyond the true entry
+            ob = o + d * t0;
+        }
+        ox = (float)ob.x; oy = (float)ob.y; oz = (float)ob.z;
+        ix = 1.0f / (float)d.x; iy = 1.0f / (float)d.y; iz = 1.0f / (float)d.z;
+        R.exact = false;
+    } else {
+        R = make_slab_ray(o, d, B.f32_ok != 0);
+        ox = R.ox; oy = R.oy; oz = R.oz; ix = R.ix; iy = R.iy; iz = R.iz;
     }
-    const float ox = (float)ob.x, oy = (float)ob.y, oz = (float)ob.z;
-    const float ix = 1.0f / (float)d.x, iy = 1.0f / (float)d.y, iz = 1.0f / (float)d.z;
+    // Float slabs in the form t = fma(plane, 1/d, -o/d) with the near and far plane of each axis picked by the sign of 1/d — per ray that
+    // is a choice of ADDRESS inside the node (lox.. or hix..), so a box costs six fused multiply-adds and four min/max instead of twelve
+    // operations and ten min/max. Rounding: the constant c = fl(-o * (1/d)) is off by u |o / d|, i.e. u |o| <= 3.8e-6 in position space, on
+    // top of the origin's own rounding (3.8e-6), the relative error 2u of 1/d over a distance <= 128 (1.5e-5) and the final rounding
+    // (7.6e-6): 3.1e-5 < CGRT_BOX_PAD, like the subtract-then-multiply form. A component of d so small that plane * (1/d) overflows
+    // gives inf - inf = NaN, which min/max drop: that axis then does not constrain the box (conservative).
+    const float cx = -(ox * ix), cy = -(oy * iy), cz = -(oz * iz);
+    const int sxo = ix < 0.f ? 3 : 0, syo = iy < 0.f ? 3 : 0, szo = iz < 0.f ? 3 : 0;  // float4 index of the near plane: lo (0) or hi (3)
     double best = tmax;
     float best_up = __double2float_ru(tmax - t0);
     int best_leaf = -1;
-    int stack[64];
+    int stack[CGRT_BVH_STACK];
     int sp = 0;
     int node = B.root_is_leaf ? ~0 : 0;
     for (;;) {
         if (node >= 0) {
-            const float4 *q = reinterpret_cast<const float4 *>(B.nodes + node);
-            float4 q0 = __ldg(q), q1 = __ldg(q + 1), q2 = __ldg(q + 2), q3 = __ldg(q + 3);
-            if (COUNT) tc->node_visits++;
-            int c0 = __float_as_int(q3.x), c1 = __float_as_int(q3.y);
-            float tn0, tn1;
-            bool h0, h1;
-            {
-                const float tx0 = (q0.x - ox) * ix, tx1 = (q0.w - ox) * ix, ty0 = (q0.y - oy) * iy, ty1 = (q1.x - oy) * iy;
-                const float tz0 = (q0.z - oz) * iz, tz1 = (q1.y - oz) * iz;
-                tn0 = fmaxf(fmaxf(fminf(tx0, tx1), fminf(ty0, ty1)), fmaxf(fminf(tz0, tz1), 0.0f));
-                h0 = tn0 <= fminf(fminf(fmaxf(tx0, tx1), fmaxf(ty0, ty1)), fminf(fmaxf(tz0, tz1), best_up));
-            }
-            {
-                const float tx0 = (q1.z - ox) * ix, tx1 = (q2.y - ox) * ix, ty0 = (q1.w - oy) * iy, ty1 = (q2.z - oy) * iy;
-                const float tz0 = (q2.x - oz) * iz, tz1 = (q2.w - oz) * iz;
-                tn1 = fmaxf(fmaxf(fminf(tx0, tx1), fminf(ty0, ty1)), fmaxf(fminf(tz0, tz1), 0.0f));
-                h1 = tn1 <= fminf(fminf(fmaxf(tx0, tx1), fmaxf(ty0, ty1)), fminf(fmaxf(tz0, tz1), best_up));
-            }
-            if (h0 && h1) {
-                if (tn1 < tn0) { int tmp = c0; c0 = c1; c1 = tmp; }
-                stack[sp++] = c1;
-                node = c0;
-            } else if (h0) {
-                node = c0;
-            } else if (h1) {
-                node = c1;
+            const float4 *q = reinterpret_cast<const float4 *>(B.nodes4 + node);
+            const int4 ch = __ldg(reinterpret_cast<const int4 *>(q + 6));
+            if (COUNT) tc->node_visits += 4;
+            unsigned int key[4];
+            if (!F32ONLY && R.exact) {
+                const float4 lx = __ldg(q), ly = __ldg(q + 1), lz = __ldg(q + 2), hx = __ldg(q + 3), hy = __ldg(q + 4), hz = __ldg(q + 5);
+#pragma unroll
+                for (int j = 0; j < 4; j++) {
+                    float tn;
+                    const bool h = slab64(f4c(lx, j), f4c(ly, j), f4c(lz, j), f4c(hx, j), f4c(hy, j), f4c(hz, j), R, best, tn);
+                    key[j] = h ? ((__float_as_uint(tn) & ~3u) | (unsigned int)j) : 0xffffffffu;
+                }
             } else {
+                const float4 nx = __ldg(q + sxo), fx = __ldg(q + 3 - sxo), ny = __ldg(q + 1 + syo), fy = __ldg(q + 4 - syo);
+                const float4 nz = __ldg(q + 2 + szo), fz = __ldg(q + 5 - szo);
+#pragma unroll
+                for (int j = 0; j < 4; j++) {
+                    const float tn = fmaxf(fmaxf(fmaf(f4c(nx, j), ix, cx), fmaf(f4c(ny, j), iy, cy)), fmaxf(fmaf(f4c(nz, j), iz, cz), 0.0f));
+                    const float tf = fminf(fminf(fmaf(f4c(fx, j), ix, cx), fmaf(f4c(fy, j), iy, cy)), fminf(fmaf(f4c(fz, j), iz, cz), best_up));
+                    key[j] = (tn <= tf) ? ((__float_as_uint(tn) & ~3u) | (unsigned int)j) : 0xffffffffu;  // tn >= 0: its bits order like the value
+                }
+            }
+            // empty slots hold an inverted box far outside the scene in the binary node's place: mask them by their link
+            if (ch.z == CGRT_NO_CHILD) key[2] = 0xffffffffu;
+            if (ch.w == CGRT_NO_CHILD) key[3] = 0xffffffffu;
+            cswap(key[0], key[1]); cswap(key[2], key[3]); cswap(key[0], key[2]); cswap(key[1], key[3]); cswap(key[1], key[2]);
+            if (key[0] == 0xffffffffu) {
                 if (sp == 0) break;
                 node = stack[--sp];
+            } else {
+                // links of the sorted slots, without branches; the stack takes the far ones, farthest first
+                int c[4];
+#pragma unroll
+                for (int k = 0; k < 4; k++) {
+                    // ch[slot] by funnel shifts (a clamped shift by 32 picks the high word): no branches, no local-memory indexing
+                    const unsigned int s1 = (key[k] & 1u) << 5, s2 = (key[k] & 2u) << 4;
+                    const unsigned int lo = __funnelshift_rc((unsigned int)ch.x, (unsigned int)ch.y, s1);
+                    const unsigned int hi = __funnelshift_rc((unsigned int)ch.z, (unsigned int)ch.w, s1);
+                    c[k] = (int)__funnelshift_rc(lo, hi, s2);
+                }
+                if (key[3] != 0xffffffffu) stack[sp++] = c[3];
+                if (key[2] != 0xffffffffu) stack[sp++] = c[2];
+                if (key[1] != 0xffffffffu) stack[sp++] = c[1];
+                node = c[0];
             }
         } else {
-            int leaf = ~node;
+            const int leaf = ~node;
             if (COUNT) tc->tri_tests++;
             double t;
             if (tri_intersect(B.tris + leaf, o, d, t) && t < best) {
@@ -782,7 +754,7 @@ __device__ __forceinline__ bool deferred_resolve(const SceneDev &S, int i, d3 o,
         return false;
     }
     double t; int leaf;
-    if (!(F32 ? bvh_closest_f32<COUNT>(S.bvh[O.bvh], o, d, lim, t, leaf, tc) : bvh_closest<COUNT>(S.bvh[O.bvh], o, d, lim, t, leaf, tc))) return false;
+    if (!bvh4_closest<COUNT, F32>(S.bvh[O.bvh], o, d, lim, t, leaf, tc)) return false;
     bvh_merge(S, i, leaf, t, A);
     return true;
 }

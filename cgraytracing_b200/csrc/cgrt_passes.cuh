@@ -353,22 +353,25 @@ __global__ void __launch_bounds__(128, CGRT_TRAV_MINB) photon_traverse_kernel(co
     TravCounters tcl;
     tcl.node_visits = 0; tcl.tri_tests = 0;
     for (unsigned int i = blockIdx.x * blockDim.x + threadIdx.x; i < total; i += gridDim.x * blockDim.x) {
-        const double2 *p = reinterpret_cast<const double2 *>(q + i);
-        double2 q0 = p[0], q1 = p[1], q2 = p[2];
-        d3 o = mk(q0.x, q0.y, q1.x), d = mk(q1.y, q2.x, q2.y);
-        HitAcc A;
-        A.nearest = q[i].nearest; A.id = q[i].id; A.prim = -1; A.nrm = mk(0, 0, 0);
-        bool changed = false;
+        // Only (nearest, id) of the running closest hit stay in registers across a traversal; the ray is re-read from the queue entry
+        // (L1) for every tree, and a closer hit is written back at once.
+        double nearest = q[i].nearest;
+        int id = q[i].id;
         for (int k = 0; k < S.nobj; k++) {
             if (S.obj[k].bvh < 0) continue;  // Bezier objects were resolved by photon_bezier_kernel
+            const double2 *p = reinterpret_cast<const double2 *>(q + i);
+            double2 q0 = p[0], q1 = p[1], q2 = p[2];
+            d3 o = mk(q0.x, q0.y, q1.x), d = mk(q1.y, q2.x, q2.y);
+            HitAcc A;
+            A.nearest = nearest; A.id = id; A.prim = -1; A.nrm = mk(0, 0, 0);
             double lim;
             if (!deferred_wanted(S, k, o, d, A, lim)) continue;
-            changed |= deferred_resolve<COUNT, false, F32>(S, k, o, d, lim, A, &tcl);
-        }
-        if (changed) {
-            q[i].nearest = A.nearest;
-            q[i].nrm[0] = A.nrm.x; q[i].nrm[1] = A.nrm.y; q[i].nrm[2] = A.nrm.z;
-            q[i].id = A.id; q[i].prim = A.prim;
+            if (deferred_resolve<COUNT, false, F32>(S, k, o, d, lim, A, &tcl)) {
+                nearest = A.nearest; id = A.id;
+                q[i].nearest = A.nearest;
+                q[i].nrm[0] = A.nrm.x; q[i].nrm[1] = A.nrm.y; q[i].nrm[2] = A.nrm.z;
+                q[i].id = A.id; q[i].prim = A.prim;
+            }
         }
     }
     if (COUNT) {

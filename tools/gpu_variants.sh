@@ -6,6 +6,6 @@ for v in ${VARIANTS:-A B}; do
   python - <<PY
 import json
 d=json.load(open('gpurun_out/bench_var_$v.json'))
-print('variant $v ${!ev}', 'value', round(d['value']/1e6,1), 'ms', round(d['ms_per_step'],2), {a.split('<')[-1][:8]: round(b,2) for a,b in d['kernels']['photon_trace_kernel']['split_ms'].items()}, 'deposit', round(d['kernels']['photon_deposit_kernel']['seconds']*1e3,2), 'sort', round(d['kernels']['bin_scan+bin_scatter_kernel']['seconds']*1e3,3))
+print('variant $v ${!ev}', 'value', round(d['value']/1e6,1), 'ms', round(d['ms_per_step'],2), {a.split('<')[-1][:8]: round(b,2) for a,b in d['kernels']['photon_trace_family']['split_ms'].items()}, 'deposit', round(d['kernels']['photon_deposit_kernel']['seconds']*1e3,2), 'sort', round(d['kernels']['bin_scan+bin_scatter_kernel']['seconds']*1e3,3))
 PY
 done
