@@ -780,6 +780,10 @@ __global__ void __launch_bounds__(CGRT_DEPOSIT_BLOCK, CGRT_DEPOSIT_MINB) photon_
     unsigned int ndep = 0, npair = 0, ngroup = 0, nstaged = 0;
     const int idx = lane / 9, idy = (lane / 3) % 3, idz = lane % 3;  // idx outermost, idz innermost (main.cpp:110-112)
     int qn = 0;
+    // the candidate list staged last: its cell, its length, the cell's raw candidate count, and whether it is the cell's complete list
+    int st_cx = 0, st_cy = 0, st_cz = 0, st_nc = 0;
+    uint32_t st_total = 0;
+    bool st_ok = false;
     const size_t n_slots = (size_t)__ldg(n_valid);
     if (blockIdx.x == 0 && threadIdx.x == 0) atomicAdd(&ctr->gathered_hits, (unsigned long long)n_slots);
     // one exact step: 32 queued pairs (fewer at the end of a stage), one per lane
@@ -834,69 +838,83 @@ __global__ void __launch_bounds__(CGRT_DEPOSIT_BLOCK, CGRT_DEPOSIT_MINB) photon_
                 const bool in_grp = valid && ix == cx && iy == cy && iz == cz;
                 const unsigned int grp = __ballot_sync(0xffffffffu, in_grp) & remaining;
                 remaining &= ~grp;
-                // the 27 bucket ranges of this cell (main.cpp:105-113)
-                uint32_t beg = 0, cnt = 0;
-                if (lane < 27) {
-                    uint32_t key = cell_hash(cx - 1 + idx, cy - 1 + idy, cz - 1 + idz, P.hashsize);
-                    beg = __ldg(cell_start + key);
-                    cnt = __ldg(cell_start + key + 1) - beg;
-                }
-                uint32_t incl = cnt;
+                // A cell's records are consecutive in the sorted order, so the batch that follows usually starts with the cell this one ended
+                // with: when the candidates staged last belong to the same cell and were the cell's whole (culled) list, they are used again
+                // as they are — the 27 bucket ranges, the filter records and the cull are read and done once per run of a cell, not per batch.
+                const bool reuse = st_ok && cx == st_cx && cy == st_cy && cz == st_cz;  // warp-uniform
+                uint32_t beg = 0, cnt = 0, excl = 0, total = st_total;
+                if (!reuse) {
+                    // the 27 bucket ranges of this cell (main.cpp:105-113)
+                    if (lane < 27) {
+                        uint32_t key = cell_hash(cx - 1 + idx, cy - 1 + idy, cz - 1 + idz, P.hashsize);
+                        beg = __ldg(cell_start + key);
+                        cnt = __ldg(cell_start + key + 1) - beg;
+                    }
+                    uint32_t incl = cnt;
 #pragma unroll
-                for (int o = 1; o < 32; o <<= 1) {
-                    uint32_t y = __shfl_up_sync(0xffffffffu, incl, o);
-                    if (lane >= o) incl += y;
+                    for (int o = 1; o < 32; o <<= 1) {
+                        uint32_t y = __shfl_up_sync(0xffffffffu, incl, o);
+                        if (lane >= o) incl += y;
+                    }
+                    excl = incl - cnt;
+                    total = __shfl_sync(0xffffffffu, incl, 31);
+                    if (lane == 0) { ngroup++; nstaged += total; }
+                    st_ok = false;  // the staged list is about to be overwritten
                 }
-                const uint32_t excl = incl - cnt;
-                const uint32_t total = __shfl_sync(0xffffffffu, incl, 31);
                 cand_total += (lane == 0) ? (unsigned long long)total * (unsigned int)__popc(grp) : 0ull;
-                if (lane == 0) { ngroup++; nstaged += total; }
                 // the cell of this group as a float box (a hair larger): a candidate whose sphere does not reach the box cannot accept
                 // any hit of the group and is dropped once per group instead of being tested against every hit
                 const float bx0 = (float)(-35.0 + (double)cx * P.celllength), by0 = (float)(-35.0 + (double)cy * P.celllength),
                             bz0 = (float)(-15.0 + (double)cz * P.celllength), bw = (float)P.celllength;
                 const float bm = 1e-5f * (fabsf(bx0) + fabsf(by0) + fabsf(bz0) + bw + 1.0f);
-                for (uint32_t c0 = 0; c0 < total; c0 += 64) {
-                    // ---- stage up to 64 candidates of the concatenated bucket lists
-                    int nc = 0;
+                uint32_t c0 = 0;       // raw candidates consumed so far
+                bool first_list = true;
+                for (;;) {
+                    int nc = st_nc;
+                    if (!reuse) {
+                        // ---- stage: append the survivors of 32 raw candidates at a time until more than 32 are listed (the list holds 64)
+                        nc = 0;
+                        while (c0 < total && nc <= 32) {
+                            const uint32_t c = c0 + lane;
+                            c0 += 32;
+                            int lo = 0;  // owner bucket of candidate c = last lane < 27 whose excl <= c (shuffle binary search)
 #pragma unroll
-                    for (int h = 0; h < 2; h++) {
-                        const uint32_t c = c0 + 32 * h + lane;
-                        int lo = 0;  // owner bucket of candidate c = last lane < 27 whose excl <= c (shuffle binary search)
-#pragma unroll
-                        for (int step_ = 16; step_ >= 1; step_ >>= 1) {
-                            int probe = lo + step_;
-                            uint32_t e = __shfl_sync(0xffffffffu, excl, probe & 31);
-                            if (probe < 27 && e <= c) lo = probe;
+                            for (int step_ = 16; step_ >= 1; step_ >>= 1) {
+                                int probe = lo + step_;
+                                uint32_t e = __shfl_sync(0xffffffffu, excl, probe & 31);
+                                if (probe < 27 && e <= c) lo = probe;
+                            }
+                            const uint32_t e_lo = __shfl_sync(0xffffffffu, excl, lo);
+                            const uint32_t b_lo = __shfl_sync(0xffffffffu, beg, lo);
+                            bool keep = false;
+                            uint32_t hidx = 0;
+                            float4 q = make_float4(0.f, 0.f, 0.f, -1.f), q_n = q, q_f = q;
+                            if (c < total) {
+                                hidx = b_lo + (c - e_lo);
+                                q = __ldg(pre + hidx);
+                                q_n = __ldg(pre_n + hidx);
+                                if (ACC == 1) q_f = __ldg(pre_f + hidx);
+                                const float ex = fmaxf(fmaxf(bx0 - bm - q.x, q.x - (bx0 + bw + bm)), 0.f);
+                                const float ey = fmaxf(fmaxf(by0 - bm - q.y, q.y - (by0 + bw + bm)), 0.f);
+                                const float ez = fmaxf(fmaxf(bz0 - bm - q.z, q.z - (bz0 + bw + bm)), 0.f);
+                                keep = fmaf(ez, ez, fmaf(ey, ey, ex * ex)) <= q.w;
+                            }
+                            const unsigned int km = __ballot_sync(0xffffffffu, keep);
+                            if (keep) {
+                                const int at = nc + __popc(km & lt);
+                                cpre[at] = q;
+                                cnrm[at] = q_n;
+                                if (ACC == 1) cf[at] = q_f;
+                                cidx[at] = hidx;
+                            }
+                            nc += __popc(km);
                         }
-                        const uint32_t e_lo = __shfl_sync(0xffffffffu, excl, lo);
-                        const uint32_t b_lo = __shfl_sync(0xffffffffu, beg, lo);
-                        bool keep = false;
-                        uint32_t hidx = 0;
-                        float4 q = make_float4(0.f, 0.f, 0.f, -1.f), q_n = q, q_f = q;
-                        if (c < total) {
-                            hidx = b_lo + (c - e_lo);
-                            q = __ldg(pre + hidx);
-                            q_n = __ldg(pre_n + hidx);
-                            if (ACC == 1) q_f = __ldg(pre_f + hidx);
-                            const float ex = fmaxf(fmaxf(bx0 - bm - q.x, q.x - (bx0 + bw + bm)), 0.f);
-                            const float ey = fmaxf(fmaxf(by0 - bm - q.y, q.y - (by0 + bw + bm)), 0.f);
-                            const float ez = fmaxf(fmaxf(bz0 - bm - q.z, q.z - (bz0 + bw + bm)), 0.f);
-                            keep = fmaf(ez, ez, fmaf(ey, ey, ex * ex)) <= q.w;
-                        }
-                        const unsigned int km = __ballot_sync(0xffffffffu, keep);
-                        if (keep) {
-                            const int at = nc + __popc(km & lt);
-                            cpre[at] = q;
-                            cnrm[at] = q_n;
-                            if (ACC == 1) cf[at] = q_f;
-                            cidx[at] = hidx;
-                        }
-                        nc += __popc(km);
+                        // pad the staged list to a multiple of 8 with records no hit can pass, so that the scan runs in unguarded blocks of 8
+                        if (lane < 8 && nc + lane < ((nc + 7) & ~7)) cpre[nc + lane] = make_float4(0.f, 0.f, 0.f, -1.f);
+                        __syncwarp();
+                        if (c0 >= total && first_list) { st_ok = true; st_cx = cx; st_cy = cy; st_cz = cz; st_nc = nc; st_total = total; }
+                        first_list = false;
                     }
-                    // pad the staged list to a multiple of 8 with records no hit can pass, so that the scan runs in unguarded blocks of 8
-                    if (lane < 8 && nc + lane < ((nc + 7) & ~7)) cpre[nc + lane] = make_float4(0.f, 0.f, 0.f, -1.f);
-                    __syncwarp();
                     // ---- prefilter: every lane tests its own hit against the staged candidates (shared-memory broadcast)
                     unsigned int m_lo = 0, m_hi = 0;
                     {
@@ -945,6 +963,7 @@ __global__ void __launch_bounds__(CGRT_DEPOSIT_BLOCK, CGRT_DEPOSIT_MINB) photon_
                     step(0, qn);
                     qn = 0;
                     __syncwarp();
+                    if (reuse || c0 >= total) break;
                 }
             }
         }
