@@ -91,8 +91,8 @@ def test_cpp_two_gpu_render_equals_one_gpu(host_bins, tmp_path):
     assets = os.path.join(ROOT, "cgraytracing_b200", "assets")
     outs = []
     for gpus in (1, 2):
-        o = subprocess.check_output([exe, "bunny", "160", "120", "60001", "3", str(tmp_path / f"o{gpus}.ppm"), assets, str(gpus)], text=True).split()
-        outs.append(o)
+        o = subprocess.check_output([exe, "bunny", "160", "120", "60001", "3", str(tmp_path / f"o{gpus}.ppm"), assets, str(gpus)], text=True)
+        outs.append(o.strip().splitlines()[-1].split())  # the last line is the program's (NCCL prints its version banner on stdout first)
     assert outs[0][0] == outs[1][0] and outs[0][1] == outs[1][1] and int(outs[0][1]) > 0   # hitpoints, deposits
     a, b = (np.frombuffer((tmp_path / f"o{g}.ppm").read_bytes()[-160 * 120 * 3:], np.uint8) for g in (1, 2))
     assert np.abs(a.astype(int) - b.astype(int)).max() <= 1   # fp64 atomics + all-reduce order: identical up to rare +-1 levels
