@@ -35,7 +35,7 @@ ABI_SYMBOLS = [
 class CgrtConfig(C.Structure):
     _fields_ = [
         ("width", C.c_int32), ("height", C.c_int32), ("max_depth", C.c_int32), ("num_of_samples", C.c_int32), ("use_dof", C.c_int32),
-        ("hashsize", C.c_int32), ("accum_mode", C.c_int32), ("reserved", C.c_int32),
+        ("hashsize", C.c_int32), ("accum_mode", C.c_int32), ("update_mode", C.c_int32),
         ("alpha", C.c_double), ("focus_plane", C.c_double), ("lens_radius", C.c_double),
         ("lightorg", C.c_double * 3), ("camorg", C.c_double * 3), ("seed", C.c_uint64),
     ]
@@ -123,6 +123,7 @@ class Context:
         for f in ("width", "height", "max_depth", "num_of_samples", "use_dof", "hashsize"):
             setattr(k, f, int(getattr(cfg, f)))
         k.accum_mode = int(getattr(cfg, "accum_mode", 0) if accum_mode is None else accum_mode)
+        k.update_mode = int(getattr(cfg, "update_mode", 1))  # 0: the reference's per-photon update (U1), 1: per round (U2)
         k.alpha, k.focus_plane, k.lens_radius = cfg.alpha, cfg.focus_plane, cfg.lens_radius
         k.lightorg = (C.c_double * 3)(*cfg.lightorg)
         k.camorg = (C.c_double * 3)(*cfg.camorg)

@@ -242,6 +242,10 @@ struct cgrt_ctx {
     // hits of one chunk that fall into it, so at 4096^2 (16x the cells of 1024^2) a 16 Mi chunk left ~2 hits per cell group and the
     // kernel re-read 88 GB of candidates per chunk
     size_t photon_chunk = 0;
+    // per-photon update (update_mode 0): r2 after n accepted photons, the reference's recurrence r2 *= (n a + a) / (n a + 1) run on the host
+    double *r2tab = nullptr;
+    int r2cap = 0;
+    int *d_maxcnt = nullptr;
     size_t auto_chunk = 0;
     int counting = 0;  // 1: photon trace kernels also count BVH node visits / triangle tests (roofline accounting)
 };
@@ -684,6 +688,7 @@ void cgrt_default_config(cgrt_config *c) {
     memset(c, 0, sizeof *c);
     c->width = 1024; c->height = 768; c->max_depth = 5; c->num_of_samples = 1; c->use_dof = 0; c->hashsize = 1000001;
     c->accum_mode = 0;
+    c->update_mode = 1;
     c->alpha = 0.7; c->focus_plane = 20.0; c->lens_radius = 1.5;
     c->lightorg[0] = 0; c->lightorg[1] = 19.999; c->lightorg[2] = 20;
     c->camorg[0] = 0; c->camorg[1] = 0; c->camorg[2] = -10;
@@ -797,7 +802,10 @@ int cgrt_set_config(cgrt_ctx *ctx, const cgrt_config *cfg) {
         FAIL(CGRT_ERR_CAPACITY, "config: width*height*samples must be < 2^28 (creation sequence is 32 bits)");
     if (cfg->max_depth > 5) FAIL(CGRT_ERR_CAPACITY, "config: max_depth > 5 needs more than 4 DFS bits");
     if (ctx->hp_count) FAIL(CGRT_ERR_INVALID, "config cannot change after the eye pass");
+    if (cfg->update_mode != 0 && cfg->update_mode != 1) FAIL(CGRT_ERR_INVALID, "config: update_mode must be 0 (per photon) or 1 (per round)");
+    if (cfg->update_mode == 0 && ctx->comm) FAIL(CGRT_ERR_INVALID, "config: the per-photon update is not shard-invariant (one GPU only)");
     ctx->cfg = *cfg;
+    if (cfg->update_mode == 0) ctx->cfg.accum_mode = 0;  // per-photon update: fp64 sums S = sum c / r2_old in the accumulator buffer
     derive_params(ctx);
     return CGRT_OK;
 }
@@ -1164,6 +1172,24 @@ int cgrt_import_hitpoints_dev(cgrt_ctx *ctx, const void *records_dev, int64_t co
     return CGRT_OK;
 }
 
+// Per-photon update: (re)build the table r2(n), n < cap, with the reference's own statements (main.cpp:119-120) on the host.
+static int build_r2_table(cgrt_ctx *ctx, int cap) {
+    std::vector<double> t((size_t)cap);
+    double r2 = ctx->P.r2_init;
+    const double alpha = ctx->P.alpha;
+    for (int n = 0; n < cap; n++) {
+        t[(size_t)n] = r2;
+        double g = (n * alpha + alpha) / (n * alpha + 1.0);
+        r2 *= g;
+    }
+    if (ctx->r2tab) CKS(dfree(ctx, ctx->r2tab));
+    CKS(dalloc(ctx, &ctx->r2tab, (size_t)cap));
+    CK(cudaMemcpyAsync(ctx->r2tab, t.data(), (size_t)cap * sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
+    CK(cudaStreamSynchronize(ctx->stream));
+    ctx->r2cap = cap;
+    return CGRT_OK;
+}
+
 // ---- grid ----------------------------------------------------------------------------------------------------------
 int cgrt_build_grid(cgrt_ctx *ctx) {
     if (!ctx) return CGRT_ERR_INVALID;
@@ -1195,6 +1221,11 @@ int cgrt_build_grid(cgrt_ctx *ctx) {
         ctx->A.f = reinterpret_cast<double *>(slab + o_f);
         ctx->acc = slab + o_acc;
         CK(cudaMemsetAsync(ctx->acc, 0, acc_bytes ? acc_bytes : 1, ctx->stream));
+    }
+    if (ctx->cfg.update_mode == 0) {
+        CKS(build_r2_table(ctx, 1 << 20));
+        CKS(dalloc(ctx, &ctx->d_maxcnt, 1));
+        CK(cudaMemsetAsync(ctx->d_maxcnt, 0, sizeof(int), ctx->stream));
     }
     CKS(dalloc(ctx, &ctx->A.flux, (size_t)n * 4));
     CKS(dalloc(ctx, &ctx->A.cnt, (size_t)n));
@@ -1358,12 +1389,17 @@ int cgrt_photon_pass(cgrt_ctx *ctx, uint64_t first, uint64_t count) {
             size_t spans = (slots + CGRT_DEPOSIT_SPAN - 1) / CGRT_DEPOSIT_SPAN;
             size_t want = (spans * 32 + CGRT_DEPOSIT_BLOCK - 1) / CGRT_DEPOSIT_BLOCK;
             unsigned int dblocks = (unsigned int)(want < (size_t)ctx->deposit_grid ? want : (size_t)ctx->deposit_grid);
-            if (ctx->cfg.accum_mode == 0)
+            U1State U1;
+            U1.cnt = ctx->A.cnt; U1.r2tab = ctx->r2tab; U1.cap = ctx->r2cap;
+            if (ctx->cfg.update_mode == 0)
+                photon_deposit_kernel<2><<<dblocks, CGRT_DEPOSIT_BLOCK, 0, D>>>(P, B.rec, B.perm, B.nvalid, ctx->cell_start, ctx->A.pre, ctx->A.pre_n,
+                                                                                ctx->A.pre_f, ctx->A.hot, ctx->A.f, ctx->acc, ctx->d_ctr, U1);
+            else if (ctx->cfg.accum_mode == 0)
                 photon_deposit_kernel<0><<<dblocks, CGRT_DEPOSIT_BLOCK, 0, D>>>(P, B.rec, B.perm, B.nvalid, ctx->cell_start, ctx->A.pre, ctx->A.pre_n,
-                                                                                ctx->A.pre_f, ctx->A.hot, ctx->A.f, ctx->acc, ctx->d_ctr);
+                                                                                ctx->A.pre_f, ctx->A.hot, ctx->A.f, ctx->acc, ctx->d_ctr, U1);
             else
                 photon_deposit_kernel<1><<<dblocks, CGRT_DEPOSIT_BLOCK, 0, D>>>(P, B.rec, B.perm, B.nvalid, ctx->cell_start, ctx->A.pre, ctx->A.pre_n,
-                                                                                ctx->A.pre_f, ctx->A.hot, ctx->A.f, ctx->acc, ctx->d_ctr);
+                                                                                ctx->A.pre_f, ctx->A.hot, ctx->A.f, ctx->acc, ctx->d_ctr, U1);
             ctx->launches++;
         } else if (ctx->profiling) {
             CK(cudaEventRecord(e[2], D));
@@ -1436,6 +1472,7 @@ int cgrt_allreduce_accum(cgrt_ctx *ctx, void *nccl_comm) {
 
 int cgrt_set_comm(cgrt_ctx *ctx, void *nccl_comm, int world) {
     if (!ctx || world < 1) return CGRT_ERR_INVALID;
+    if (nccl_comm && ctx->cfg.update_mode == 0) FAIL(CGRT_ERR_INVALID, "the per-photon update is not shard-invariant (one GPU only)");
     if (nccl_comm && !nccl_api().ok) FAIL(CGRT_ERR_NCCL, "NCCL is not available: " + nccl_api().why);
     CKS(join_update(ctx));
     ctx->comm = nccl_comm;
@@ -1532,7 +1569,21 @@ int cgrt_round_update(cgrt_ctx *ctx) {
         CK(cudaStreamWaitEvent(U, ctx->ev_tail, 0));
     }
     if (ctx->comm) CKS(allreduce_on(ctx, ctx->comm, U));
-    if (n > 0) {
+    if (n > 0 && ctx->cfg.update_mode == 0) {
+        // per-photon update: fold the live counts into r2 / flux / filter radii; grow the r2 table before any count can reach its end
+        round_update_u1_kernel<<<nblk(n, 256), 256, 0, U>>>(n, ctx->A, reinterpret_cast<const double *>(ctx->acc), ctx->r2tab, ctx->r2cap, ctx->d_maxcnt);
+        ctx->launches++;
+        int maxcnt = 0;
+        CK(cudaMemcpyAsync(&maxcnt, ctx->d_maxcnt, sizeof maxcnt, cudaMemcpyDeviceToHost, U));
+        CK(cudaStreamSynchronize(U));
+        if (maxcnt >= ctx->r2cap - 1) FAIL(CGRT_ERR_CAPACITY, "per-photon update: a hitpoint accepted more photons in one round than the r2 table holds");
+        if (maxcnt > ctx->r2cap / 4) {
+            CK(cudaStreamSynchronize(ctx->stream));
+            int cap = ctx->r2cap;
+            while (maxcnt > cap / 4 && cap < (1 << 28)) cap *= 2;
+            CKS(build_r2_table(ctx, cap));
+        }
+    } else if (n > 0) {
         if (ctx->cfg.accum_mode == 0) round_update_kernel<0><<<nblk(n, 256), 256, 0, U>>>(n, ctx->P.alpha, ctx->A, ctx->acc);
         else round_update_kernel<1><<<nblk(n, 256), 256, 0, U>>>(n, ctx->P.alpha, ctx->A, ctx->acc);
         ctx->launches++;

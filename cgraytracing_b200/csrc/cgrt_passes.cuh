@@ -664,6 +664,9 @@ struct HitShared<1> {
     uint32_t src[32]; // slot of the record in the deposit table
 };
 
+template <>
+struct HitShared<2> : HitShared<0> {};  // per-photon update: fp64 records like ACC 0
+
 struct ExactHit {  // the fp64 photon side of one pair
     d3 X, nrm, flux;
 };
@@ -672,6 +675,7 @@ __device__ __forceinline__ ExactHit exact_hit(const HitShared<0> &H, uint32_t hl
     e.X = mk(H.v[0][hl], H.v[1][hl], H.v[2][hl]); e.nrm = mk(H.v[3][hl], H.v[4][hl], H.v[5][hl]); e.flux = mk(H.v[6][hl], H.v[7][hl], H.v[8][hl]);
     return e;
 }
+__device__ __forceinline__ ExactHit exact_hit(const HitShared<2> &H, uint32_t hl, const DepositRec *r) { return exact_hit(static_cast<const HitShared<0> &>(H), hl, r); }
 __device__ __forceinline__ ExactHit exact_hit(const HitShared<1> &H, uint32_t hl, const DepositRec *__restrict__ rec) {
     const double4 *r = reinterpret_cast<const double4 *>(rec + H.src[hl]);
     double4 r0 = ldg4(r), r1 = ldg4(r + 1), r2 = ldg4(r + 2);
@@ -711,6 +715,44 @@ __device__ __forceinline__ void deposit_exact(const ExactHit &e, uint32_t hidx, 
     }
 }
 
+// The reference's own update rule (main.cpp:116-122, SURVEY Q1 "U1"): an accepted photon shrinks the hitpoint's radius AT ONCE, and the
+// next photon is tested against the shrunk radius. r2 is a function of the accepted count alone — r2(n+1) = r2(n) (n a + a) / (n a + 1)
+// from the common start (200/height)^2 — so the live state of a hitpoint is one integer: the test reads r2 from a table of the
+// reference's recurrence (built on the host in the reference's arithmetic) and an acceptance is a compare-and-swap n -> n+1; a lost race
+// re-tests against the newer radius. The reference's flux recurrence flux = (flux + c) g telescopes to flux = r2(n_final) * sum_k c_k /
+// r2(n_k): the sums S = sum c / r2_old are accumulated here (fp64 atomics), cgrt_round_update multiplies by the current r2. Photon order
+// is arbitrary, as it is between the reference's own racing threads.
+struct U1State {
+    int *cnt;              // accepted photons per hitpoint (HpArrays::cnt, live)
+    const double *r2tab;   // r2 after n accepted photons, n < cap
+    int cap;
+};
+__device__ __forceinline__ void deposit_u1(const ExactHit &e, uint32_t hidx, const HpHot *__restrict__ hot, const double *__restrict__ hp_f,
+                                           void *__restrict__ acc, const U1State &U, unsigned int &ndep) {
+    const double2 *hp = reinterpret_cast<const double2 *>(hot + hidx);
+    double2 a0 = __ldg(hp), a1 = __ldg(hp + 1), b0 = __ldg(hp + 2), b1 = __ldg(hp + 3);  // pos and normal never change (r2 in the record is the round-start one)
+    d3 hpos = mk(a0.x, a0.y, a1.x), hn = mk(b0.x, b0.y, b1.x);
+    if (!(dot(hn, e.nrm) > CGRT_EPS)) return;
+    d3 dd = hpos - e.X;
+    const double d2 = dot(dd, dd);
+    int n_old = *reinterpret_cast<volatile int *>(U.cnt + hidx);
+    for (;;) {
+        const double r2 = U.r2tab[n_old < U.cap ? n_old : U.cap - 1];
+        if (!(d2 <= r2)) return;  // main.cpp:116 against the radius of THIS moment; a later (smaller) radius rejects as well
+        const int prev = atomicCAS(U.cnt + hidx, n_old, n_old + 1);
+        if (prev == n_old) {
+            const double2 *fp = reinterpret_cast<const double2 *>(hp_f + 4 * (size_t)hidx);
+            double2 f0 = __ldg(fp), f1 = __ldg(fp + 1);
+            d3 cc = (mk(f0.x, f0.y, f1.x) * e.flux) * (1.0 / CGRT_PI);  // f.mul(flux) * (1/PI), main.cpp:122
+            double *ap = reinterpret_cast<double *>(acc) + 4 * (size_t)hidx;
+            atomicAdd(ap, cc.x / r2); atomicAdd(ap + 1, cc.y / r2); atomicAdd(ap + 2, cc.z / r2);
+            ndep++;
+            return;
+        }
+        n_old = prev;
+    }
+}
+
 // One pair that passed the prefilter. Its outcome is decided in fp32 from shared memory whenever the rounding bounds allow it:
 //   distance   s = |fl(hp) - fl(X)|^2 <= (r - E)^2 proves dot(dd, dd) <= r2 (prefilter_inner); the prefilter already had s <= (r + E)^2
 //   normals    |fl-dot - dot| <= 5 * 2^-24 * sum |hn_i * nrm_i| (two input roundings and the float evaluation); 1e-6 * sum + 1e-9
@@ -721,7 +763,11 @@ __device__ __forceinline__ void deposit_exact(const ExactHit &e, uint32_t hidx, 
 template <int ACC>
 __device__ __forceinline__ void deposit_pair(const HitShared<ACC> &H, uint32_t hl, uint32_t hidx, float4 q, float4 qn, float4 qf,
                                              const DepositRec *__restrict__ rec, const HpHot *__restrict__ hot, const double *__restrict__ hp_f,
-                                             void *__restrict__ acc, unsigned int &ndep) {
+                                             void *__restrict__ acc, const U1State &U, unsigned int &ndep) {
+    if (ACC == 2) {  // per-photon update: the prefilter (round-start radius) only narrows the candidates down
+        deposit_u1(exact_hit(H, hl, rec), hidx, hot, hp_f, acc, U, ndep);
+        return;
+    }
     const float ddx = q.x - H.f[0][hl], ddy = q.y - H.f[1][hl], ddz = q.z - H.f[2][hl];
     const float s = fmaf(ddz, ddz, fmaf(ddy, ddy, ddx * ddx));
     const float nx = H.f[3][hl], ny = H.f[4][hl], nz = H.f[5][hl];
@@ -737,7 +783,7 @@ __device__ __forceinline__ void deposit_pair(const HitShared<ACC> &H, uint32_t h
             const HitShared<0> &H0 = reinterpret_cast<const HitShared<0> &>(H);
             d3 cc = (mk(f0.x, f0.y, f1.x) * mk(H0.v[6][hl], H0.v[7][hl], H0.v[8][hl])) * (1.0 / CGRT_PI);
             deposit_add<0>(acc, hidx, cc);
-        } else {
+        } else if (ACC == 1) {
             const HitShared<1> &H1 = reinterpret_cast<const HitShared<1> &>(H);
             const float ipi = (float)(1.0 / CGRT_PI);
             float *ap = reinterpret_cast<float *>(acc) + 4 * (size_t)hidx;
@@ -748,7 +794,7 @@ __device__ __forceinline__ void deposit_pair(const HitShared<ACC> &H, uint32_t h
         ndep++;
         return;
     }
-    deposit_exact<ACC>(exact_hit(H, hl, rec), hidx, hot, hp_f, acc, ndep);
+    deposit_exact<ACC == 2 ? 0 : ACC>(exact_hit(H, hl, rec), hidx, hot, hp_f, acc, ndep);
 }
 
 template <int ACC>
@@ -757,7 +803,8 @@ __global__ void __launch_bounds__(CGRT_DEPOSIT_BLOCK, CGRT_DEPOSIT_MINB) photon_
                                                                             const uint32_t *__restrict__ cell_start,
                                                                             const float4 *__restrict__ pre, const float4 *__restrict__ pre_n,
                                                                             const float4 *__restrict__ pre_f, const HpHot *__restrict__ hot,
-                                                                            const double *__restrict__ hp_f, void *__restrict__ acc, Counters *ctr) {
+                                                                            const double *__restrict__ hp_f, void *__restrict__ acc, Counters *ctr,
+                                                                            const U1State U) {
     // per warp: 64 staged candidates (fp32 filter records + hitpoint index) and the queue of (record, candidate) pairs that passed
     // the prefilter
     constexpr int NW = CGRT_DEPOSIT_BLOCK / 32;
@@ -791,7 +838,7 @@ __global__ void __launch_bounds__(CGRT_DEPOSIT_BLOCK, CGRT_DEPOSIT_MINB) photon_
         if (lane < count) {
             const uint32_t e = queue[first + lane];
             const uint32_t hl = e & 31u, b = e >> 8;
-            deposit_pair<ACC>(H, hl, cidx[b], cpre[b], cnrm[b], ACC == 1 ? cf[b] : make_float4(0.f, 0.f, 0.f, 0.f), rec, hot, hp_f, acc, ndep);
+            deposit_pair<ACC>(H, hl, cidx[b], cpre[b], cnrm[b], ACC == 1 ? cf[b] : make_float4(0.f, 0.f, 0.f, 0.f), rec, hot, hp_f, acc, U, ndep);
         }
     };
     // spans are handed out from a global cursor (n_valid[1], zeroed by bin_scan_sums_kernel); the next one is requested before the
@@ -818,7 +865,7 @@ __global__ void __launch_bounds__(CGRT_DEPOSIT_BLOCK, CGRT_DEPOSIT_MINB) photon_
                 ix = (int)(uint32_t)cxy; iy = (int)(uint32_t)(cxy >> 32); iz = (int)(uint32_t)__double_as_longlong(r2.z);
                 H.f[0][lane] = hx; H.f[1][lane] = hy; H.f[2][lane] = hz;
                 H.f[3][lane] = (float)r0.w; H.f[4][lane] = (float)r1.x; H.f[5][lane] = (float)r1.y;
-                if (ACC == 0) {
+                if (ACC != 1) {
                     HitShared<0> &H0 = reinterpret_cast<HitShared<0> &>(H);
                     H0.v[0][lane] = r0.x; H0.v[1][lane] = r0.y; H0.v[2][lane] = r0.z;
                     H0.v[3][lane] = r0.w; H0.v[4][lane] = r1.x; H0.v[5][lane] = r1.y;
@@ -1079,6 +1126,24 @@ __global__ void round_update_kernel(unsigned int n, double alpha, HpArrays A, vo
         A.pre[k] = make_prefilter(hh.px, hh.py, hh.pz, hh.r2);
         A.pre_n[k].w = prefilter_inner(hh.px, hh.py, hh.pz, hh.r2);
         A.cnt[k] = cnt + (int)m;
+    }
+}
+
+// Per-photon update mode: the counts are live; a "round update" only folds them into what the next round's filters and the image read:
+// r2 = table[n], flux = S * r2 (see deposit_u1), filter radii. The sums S stay in the accumulator buffer for the whole render.
+__global__ void round_update_u1_kernel(unsigned int n, HpArrays A, const double *__restrict__ S, const double *__restrict__ r2tab, int cap, int *maxcnt) {
+    unsigned int k = blockIdx.x * blockDim.x + threadIdx.x;
+    if (k >= n) return;
+    const int cnt = A.cnt[k];
+    if (cnt > *maxcnt) atomicMax(maxcnt, cnt);
+    const double r2 = r2tab[cnt < cap ? cnt : cap - 1];
+    double *fl = A.flux + 4 * (size_t)k;
+    fl[0] = S[4 * (size_t)k] * r2; fl[1] = S[4 * (size_t)k + 1] * r2; fl[2] = S[4 * (size_t)k + 2] * r2;
+    HpHot hh = A.hot[k];
+    if (hh.r2 != r2) {
+        A.hot[k].r2 = r2;
+        A.pre[k] = make_prefilter(hh.px, hh.py, hh.pz, r2);
+        A.pre_n[k].w = prefilter_inner(hh.px, hh.py, hh.pz, r2);
     }
 }
 

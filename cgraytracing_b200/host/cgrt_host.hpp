@@ -290,6 +290,8 @@ struct RenderOptions {
     int rounds = 1;                      // per-round radius/flux updates the total is split into (reference: per photon)
     int hashsize = 1000001;              // :184
     int accum_mode = 0;                  // 0: fp64 atomics, 1: float32 x4 accumulators
+    bool per_photon_update = false;      // true: the reference's own rule, main.cpp:119-122 — every accepted photon shrinks the radius at once
+                                         // (one GPU; `rounds` then only says how often filter radii are refreshed). false: one update per round
     uint64_t seed = 20261018ull;
     int device = 0;
     int num_gpus = 1;                    // > 1: devices device .. device+num_gpus-1 of this box, one context and one host thread per GPU:
@@ -312,6 +314,7 @@ inline Image render_rank(const std::vector<Object *> &objs, const RenderOptions 
     cgrt_default_config(&cfg);
     cfg.width = opt.width; cfg.height = opt.height; cfg.num_of_samples = opt.num_of_samples; cfg.use_dof = opt.depth_of_field ? 1 : 0;
     cfg.hashsize = opt.hashsize; cfg.accum_mode = opt.accum_mode; cfg.seed = opt.seed;
+    cfg.update_mode = opt.per_photon_update ? 0 : 1;
     c.check(cgrt_set_config(c.get(), &cfg));
     for (const Object *o : objs) o->describe(c);  // object id = position in objs, like the reference's loop index (main.cpp:55)
     c.check(cgrt_commit_scene(c.get()));

@@ -39,7 +39,9 @@ typedef struct cgrt_config {
     int32_t use_dof;            /* 1: trace the thin-lens ray of main.cpp:203-207 instead of the pinhole ray of :209 */
     int32_t hashsize;           /* Hashtable(hashsize, r), main.cpp:184 */
     int32_t accum_mode;         /* 0: fp64 atomics (parity), 1: one red.global.add.v4.f32 per deposit (fast) */
-    int32_t reserved;
+    int32_t update_mode;        /* 1 (default): one radius/flux update per round against the round-start radius (SURVEY Q1 "U2", the rule that
+                                 * shards over GPUs); 0: the reference's own rule, main.cpp:119-122 — every accepted photon shrinks the radius at
+                                 * once and later photons are tested against the shrunk radius ("U1"; one GPU, fp64 accumulators) */
     double alpha;               /* main.cpp:36 */
     double focus_plane;         /* main.cpp:178 */
     double lens_radius;         /* main.cpp:179 */

@@ -2,7 +2,7 @@
 for w in c1_spheres_bezier c2_bunny_chess c4_bump_dof c5_dragon_4096; do
   extra=""
   if [ $w = c5_dragon_4096 ]; then extra="--photons 134217728 --steps 2 --warmup 1 --e2e-rounds 0"; else extra="--steps 3 --warmup 3"; fi
-  timeout 600 python bench.py --workload $w $extra --cpu-photons 100000 > gpurun_out/wl_$w.json 2> gpurun_out/wl_$w.err || { echo "FAILED $w"; tail -5 gpurun_out/wl_$w.err; }
+  timeout 600 python bench.py --workload $w $extra --cpu-photons 100000 --f64-too 0 --shipped-photons 0 > gpurun_out/wl_$w.json 2> gpurun_out/wl_$w.err || { echo "FAILED $w"; tail -5 gpurun_out/wl_$w.err; }
   python - <<PY
 import json
 try:
