@@ -27,7 +27,7 @@ ABI_SYMBOLS = [
     "cgrt_count_traversal", "cgrt_eye_pass", "cgrt_export_hitpoints_dev", "cgrt_import_hitpoints_dev", "cgrt_build_grid", "cgrt_photon_pass",
     "cgrt_accum_dev", "cgrt_allreduce_accum", "cgrt_round_update", "cgrt_gather_image", "cgrt_num_hitpoints", "cgrt_download_hitpoints",
     "cgrt_download_accum", "cgrt_download_grid", "cgrt_get_counters", "cgrt_get_timings", "cgrt_set_counting", "cgrt_set_profiling", "cgrt_set_culling", "cgrt_set_overlap", "cgrt_average_u8", "cgrt_average_f64",
-    "cgrt_check_guards", "cgrt_release_cached_memory", "cgrt_photon_chunk", "cgrt_deposit_record_bytes",
+    "cgrt_check_guards", "cgrt_release_cached_memory", "cgrt_photon_chunk", "cgrt_deposit_record_bytes", "cgrt_trace",
     "cgrt_comm_unique_id", "cgrt_comm_init_rank", "cgrt_comm_init_all", "cgrt_comm_destroy", "cgrt_allgather_hitpoints", "cgrt_set_comm",
 ]
 
@@ -238,6 +238,16 @@ class Context:
 
     def photon_pass(self, first, count):
         self._ck(self.L.cgrt_photon_pass(self.h, C.c_uint64(first), C.c_uint64(count)))
+
+    def trace(self, org, dir, weight, flag, depth=0, x=None, y=None, first_index=0):
+        """trace() of main.cpp:42 for n rays: flag True = eye rays (weight = adj, pixels x, y; before build_grid), False = photons
+        (weight = flux; after build_grid; ray k draws the random numbers of photon first_index + k)."""
+        org, dir, weight = _d(org).reshape(-1, 3), _d(dir).reshape(-1, 3), _d(weight).reshape(-1, 3)
+        n = len(org)
+        xi = None if x is None else np.ascontiguousarray(x, dtype=np.int32)
+        yi = None if y is None else np.ascontiguousarray(y, dtype=np.int32)
+        self._ck(self.L.cgrt_trace(self.h, C.c_int64(n), _p(org, c_dp), _p(dir, c_dp), _p(weight, c_dp), int(bool(flag)), int(depth), _p(xi, c_ip), _p(yi, c_ip),
+                                   C.c_uint64(first_index)))
 
     def accum_dev(self):
         ptr = C.c_void_p(); n = C.c_int64(0)

@@ -1107,6 +1107,34 @@ int cgrt_radix_sort(cgrt_ctx *ctx, int64_t n, const uint64_t *key_in, int nbits,
     return dfree(ctx, d_in);
 }
 
+// The per-depth wavefront of the eye half of trace() over the n rays in ray queue 0 (or, generate = true, the camera rays of the rows from r0).
+static int eye_wavefront(cgrt_ctx *ctx, size_t n, int depth0, int r0, bool generate) {
+    const PassParams &P = ctx->P;
+    size_t max_rays = 4u << 20;
+    int cur = 0;
+    for (int depth = depth0; depth < P.max_depth && n > 0; depth++) {
+        CKS(ensure_queue(ctx, cur ^ 1, 2 * n > max_rays ? 2 * n : max_rays));  // glass splits: at most two children per ray
+        CKS(ensure_hp_capacity(ctx, (size_t)ctx->hp_count + n));
+        CK(cudaMemsetAsync(ctx->d_qcount + (cur ^ 1), 0, sizeof(unsigned int), ctx->stream));
+        if (generate && depth == depth0)
+            eye_bounce_kernel<true><<<nblk(n, 128), 128, 0, ctx->stream>>>(ctx->S, P, depth, ctx->q[cur], (unsigned int)n, r0, ctx->q[cur ^ 1],
+                                                                           ctx->d_qcount + (cur ^ 1), ctx->hp_rec, ctx->d_hp_count, ctx->hp_cap, ctx->d_ctr);
+        else
+            eye_bounce_kernel<false><<<nblk(n, 128), 128, 0, ctx->stream>>>(ctx->S, P, depth, ctx->q[cur], (unsigned int)n, r0, ctx->q[cur ^ 1],
+                                                                            ctx->d_qcount + (cur ^ 1), ctx->hp_rec, ctx->d_hp_count, ctx->hp_cap, ctx->d_ctr);
+        ctx->launches++;
+        CK(cudaGetLastError());
+        unsigned int counts[2];
+        CK(cudaMemcpyAsync(&counts[0], ctx->d_qcount + (cur ^ 1), sizeof(unsigned int), cudaMemcpyDeviceToHost, ctx->stream));
+        CK(cudaMemcpyAsync(&counts[1], ctx->d_hp_count, sizeof(unsigned int), cudaMemcpyDeviceToHost, ctx->stream));
+        CK(cudaStreamSynchronize(ctx->stream));
+        n = counts[0];
+        ctx->hp_count = counts[1];
+        cur ^= 1;
+    }
+    return CGRT_OK;
+}
+
 // ---- eye pass ------------------------------------------------------------------------------------------------------
 int cgrt_eye_pass(cgrt_ctx *ctx, int y0, int y1) {
     if (!ctx) return CGRT_ERR_INVALID;
@@ -1125,27 +1153,7 @@ int cgrt_eye_pass(cgrt_ctx *ctx, int y0, int y1) {
     for (int r0 = y0; r0 < y1; r0 += rows_per_chunk) {
         int r1 = r0 + rows_per_chunk < y1 ? r0 + rows_per_chunk : y1;
         size_t n = (size_t)(r1 - r0) * per_row;
-        int cur = 0;
-        for (int depth = 0; depth < P.max_depth && n > 0; depth++) {
-            CKS(ensure_queue(ctx, cur ^ 1, 2 * n > max_rays ? 2 * n : max_rays));  // glass splits: at most two children per ray
-            CKS(ensure_hp_capacity(ctx, (size_t)ctx->hp_count + n));
-            CK(cudaMemsetAsync(ctx->d_qcount + (cur ^ 1), 0, sizeof(unsigned int), ctx->stream));
-            if (depth == 0)
-                eye_bounce_kernel<true><<<nblk(n, 128), 128, 0, ctx->stream>>>(ctx->S, P, depth, ctx->q[cur], (unsigned int)n, r0, ctx->q[cur ^ 1],
-                                                                               ctx->d_qcount + (cur ^ 1), ctx->hp_rec, ctx->d_hp_count, ctx->hp_cap, ctx->d_ctr);
-            else
-                eye_bounce_kernel<false><<<nblk(n, 128), 128, 0, ctx->stream>>>(ctx->S, P, depth, ctx->q[cur], (unsigned int)n, r0, ctx->q[cur ^ 1],
-                                                                                ctx->d_qcount + (cur ^ 1), ctx->hp_rec, ctx->d_hp_count, ctx->hp_cap, ctx->d_ctr);
-            ctx->launches++;
-            CK(cudaGetLastError());
-            unsigned int counts[2];
-            CK(cudaMemcpyAsync(&counts[0], ctx->d_qcount + (cur ^ 1), sizeof(unsigned int), cudaMemcpyDeviceToHost, ctx->stream));
-            CK(cudaMemcpyAsync(&counts[1], ctx->d_hp_count, sizeof(unsigned int), cudaMemcpyDeviceToHost, ctx->stream));
-            CK(cudaStreamSynchronize(ctx->stream));
-            n = counts[0];
-            ctx->hp_count = counts[1];
-            cur ^= 1;
-        }
+        CKS(eye_wavefront(ctx, n, 0, r0, true));
     }
     timer.stop();
     return CGRT_OK;
@@ -1275,7 +1283,8 @@ int cgrt_build_grid(cgrt_ctx *ctx) {
 // were suspended in front of a mesh), a 24-bit radix sort of the deposit keys, and the cell-grouped deposit kernel. No host
 // synchronisation anywhere: the pass is asynchronous on the ctx stream unless profiling is on (then the phases are
 // bracketed by events and the pass ends with one synchronise).
-int cgrt_photon_pass(cgrt_ctx *ctx, uint64_t first, uint64_t count) {
+// inj_* != nullptr: the photons are the caller's rays (device arrays, cgrt_trace) instead of emissions from the light; one launch.
+static int photon_pass_impl(cgrt_ctx *ctx, uint64_t first, uint64_t count, const double *inj_org, const double *inj_dir, const double *inj_flux, int inj_depth) {
     if (!ctx) return CGRT_ERR_INVALID;
     if (!ctx->grid_built) FAIL(CGRT_ERR_INVALID, "build the grid first");
     CK(cudaSetDevice(ctx->device));
@@ -1332,14 +1341,19 @@ int cgrt_photon_pass(cgrt_ctx *ctx, uint64_t first, uint64_t count) {
 #define LAUNCH_PT(F, GRID, QIN, NIN, QOUT, NOUT, CURSOR)                                                                            \
     photon_trace_kernel<F><<<GRID, CGRT_PHOTON_BLOCK, 0, T>>>(ctx->S, P, base, (unsigned int)n, QIN, NIN, QOUT, NOUT, B.rec, B.keys, B.hist, \
                                                              ctx->cull ? ctx->reach : nullptr, ctx->d_ctr, CURSOR)
-        {
+        if (inj_org) {
+            if (n != count) FAIL(CGRT_ERR_CAPACITY, "cgrt_trace: more rays than one launch holds");
+            stamp(-1);
+            photon_inject_kernel<<<nblk(n, 128), 128, 0, T>>>(ctx->S, (unsigned int)n, inj_depth, inj_org, inj_dir, inj_flux, ctx->pq[0], qc);
+            stamp(9);
+        } else {
             unsigned int want = nblk(n, CGRT_PHOTON_BLOCK);
             stamp(-1);
             LAUNCH_PT(true, (want < ctx->grid_first ? want : ctx->grid_first), nullptr, nullptr, ctx->pq[0], qc, qc + 6);
             stamp(9);
         }
         ctx->launches++;
-        if (ctx->S.nbvh > 0 || ctx->S.nbez > 0) {
+        if (inj_org || ctx->S.nbvh > 0 || ctx->S.nbez > 0) {
             for (int pass = 1; pass <= P.max_depth; pass++) {  // a resumed photon advances at least one segment per pass
                 PhotonState *qin = ctx->pq[(pass - 1) & 1];
                 PhotonState *qout = ctx->pq[pass & 1];
@@ -1435,6 +1449,40 @@ int cgrt_photon_pass(cgrt_ctx *ctx, uint64_t first, uint64_t count) {
         ctx->prof_marks.clear();
     }
     return CGRT_OK;
+}
+
+int cgrt_photon_pass(cgrt_ctx *ctx, uint64_t first, uint64_t count) { return photon_pass_impl(ctx, first, count, nullptr, nullptr, nullptr, 0); }
+
+int cgrt_trace(cgrt_ctx *ctx, int64_t n, const double *org, const double *dir, const double *weight, int flag, int depth, const int32_t *x, const int32_t *y,
+               uint64_t first_index) {
+    if (!ctx || n < 0 || (n > 0 && (!org || !dir || !weight))) return CGRT_ERR_INVALID;
+    if (!ctx->committed) FAIL(CGRT_ERR_INVALID, "commit the scene first");
+    if (depth < 0) FAIL(CGRT_ERR_INVALID, "negative depth");
+    if (n == 0 || depth >= ctx->P.max_depth) return CGRT_OK;  // main.cpp:46: nothing is traced beyond MAX_DEPTH
+    if (n >= (1ll << 28)) FAIL(CGRT_ERR_CAPACITY, "cgrt_trace: at most 2^28 rays per call");
+    CK(cudaSetDevice(ctx->device));
+    double *d_org, *d_dir, *d_w;
+    CKS(upload(ctx, &d_org, org, (size_t)n * 3)); CKS(upload(ctx, &d_dir, dir, (size_t)n * 3)); CKS(upload(ctx, &d_w, weight, (size_t)n * 3));
+    int rc = CGRT_OK;
+    if (flag) {  // eye ray: hitpoints are created (main.cpp:85-99), children followed (main.cpp:129-157)
+        if (ctx->grid_built) FAIL(CGRT_ERR_INVALID, "eye rays add hitpoints: trace them before cgrt_build_grid");
+        if (!x || !y) FAIL(CGRT_ERR_INVALID, "eye rays need their pixel (x, y)");
+        for (int64_t i = 0; i < n; i++)
+            if (x[i] < 0 || x[i] >= ctx->P.width || y[i] < 0 || y[i] >= ctx->P.height) FAIL(CGRT_ERR_INVALID, "pixel outside the image");
+        int32_t *d_x, *d_y;
+        CKS(upload(ctx, &d_x, x, (size_t)n)); CKS(upload(ctx, &d_y, y, (size_t)n));
+        CKS(ensure_queue(ctx, 0, (size_t)n));
+        eye_inject_kernel<<<nblk(n, 256), 256, 0, ctx->stream>>>((unsigned int)n, ctx->P.width, ctx->P.samples, d_org, d_dir, d_w, d_x, d_y, ctx->q[0]);
+        ctx->launches++;
+        rc = eye_wavefront(ctx, (size_t)n, depth, 0, false);
+        CKS(dfree(ctx, d_x)); CKS(dfree(ctx, d_y));
+    } else {     // photon: deposits into the per-round accumulators (main.cpp:101-128), bounces followed
+        CK(cudaStreamSynchronize(ctx->stream));  // the uploads, whichever stream the trace kernels run on
+        rc = photon_pass_impl(ctx, first_index, (uint64_t)n, d_org, d_dir, d_w, depth);
+        if (rc == CGRT_OK) CK(cudaStreamSynchronize(ctx->stream));
+    }
+    CKS(dfree(ctx, d_org)); CKS(dfree(ctx, d_dir)); CKS(dfree(ctx, d_w));
+    return rc;
 }
 
 int cgrt_accum_dev(cgrt_ctx *ctx, void **ptr_dev, int64_t *n_elems) {

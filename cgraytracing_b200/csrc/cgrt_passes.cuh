@@ -420,6 +420,33 @@ __global__ void __launch_bounds__(128) photon_bezier_kernel(const __grid_constan
     }
 }
 
+// trace() of main.cpp:42 called with caller-made rays (cgrt_trace). Photon rays enter the wavefront as queue entries in the state a photon is
+// suspended in: the analytic part of the closest hit done, the meshes and Bezier surfaces still to be merged by the kernels that follow.
+__global__ void photon_inject_kernel(const __grid_constant__ SceneDev S, unsigned int n, int depth, const double *__restrict__ org,
+                                     const double *__restrict__ dir, const double *__restrict__ flux, PhotonState *__restrict__ q, unsigned int *n_out) {
+    unsigned int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    d3 o = mk(org[3 * i], org[3 * i + 1], org[3 * i + 2]), d = mk(dir[3 * i], dir[3 * i + 1], dir[3 * i + 2]);
+    HitAcc A;
+    analytic_phase(S, o, d, A);
+    PhotonState e;
+    e.o[0] = o.x; e.o[1] = o.y; e.o[2] = o.z; e.d[0] = d.x; e.d[1] = d.y; e.d[2] = d.z;
+    e.flux[0] = flux[3 * i]; e.flux[1] = flux[3 * i + 1]; e.flux[2] = flux[3 * i + 2];
+    e.nearest = A.nearest; e.nrm[0] = A.nrm.x; e.nrm[1] = A.nrm.y; e.nrm[2] = A.nrm.z;
+    e.id = A.id; e.prim = A.prim; e.local = i; e.depth = (uint32_t)depth; e.pad = 0.0;
+    q[i] = e;
+    if (i == 0) *n_out = n;
+}
+// Eye rays: straight into the ray queue of eye_bounce_kernel<false>. path = (y * W + x) * samples + (k mod samples).
+__global__ void eye_inject_kernel(unsigned int n, int width, int samples, const double *__restrict__ org, const double *__restrict__ dir,
+                                  const double *__restrict__ adj, const int *__restrict__ x, const int *__restrict__ y, RayQueue q) {
+    unsigned int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    uint32_t path = ((uint32_t)y[i] * (uint32_t)width + (uint32_t)x[i]) * (uint32_t)samples + (i % (uint32_t)samples);
+    push_ray(q, i, mk(org[3 * i], org[3 * i + 1], org[3 * i + 2]), mk(dir[3 * i], dir[3 * i + 1], dir[3 * i + 2]),
+             mk(adj[3 * i], adj[3 * i + 1], adj[3 * i + 2]), path, 0u);
+}
+
 // Emission (FIRST) or continuation of suspended photons whose pending segment has been resolved by photon_traverse_kernel.
 // Persistent threads with refill: a lane whose photon ends (absorbed at the last bounce, missed, or suspended in front of a
 // mesh) takes the next photon (FIRST) / queue entry in the same loop iteration, so the warp stays full instead of idling

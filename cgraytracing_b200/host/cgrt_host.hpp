@@ -280,6 +280,20 @@ public:
 };
 
 // ---------------------------------------------------------------------------------------------------------------------
+// trace(org, dir, objs, flux, adj, flag, depth, htable, x, y) — main.cpp:42 — for a batch of rays. The scene (`objs`) and the table
+// (`htable`) are the context's: describe() the objects into it and commit first. flag = true: eye rays, weight = adj, (x, y) = pixel,
+// hitpoints are inserted (before cgrt_build_grid); flag = false: photons, weight = flux, deposits (after cgrt_build_grid), ray k draws the
+// random numbers of photon index first_index + k.
+inline void trace(const Context &c, const std::vector<Vec3> &org, const std::vector<Vec3> &dir, const std::vector<Vec3> &weight, bool flag, int depth,
+                  const std::vector<int32_t> &x = std::vector<int32_t>(), const std::vector<int32_t> &y = std::vector<int32_t>(), uint64_t first_index = 0) {
+    static_assert(sizeof(Vec3) == 3 * sizeof(double), "Vec3 is three packed doubles");
+    if (dir.size() != org.size() || weight.size() != org.size() || (flag && (x.size() != org.size() || y.size() != org.size())))
+        throw Error(CGRT_ERR_INVALID, "trace: array lengths differ");
+    c.check(cgrt_trace(c.get(), (int64_t)org.size(), org.empty() ? nullptr : org[0].data(), dir.empty() ? nullptr : dir[0].data(),
+                       weight.empty() ? nullptr : weight[0].data(), flag ? 1 : 0, depth, x.empty() ? nullptr : x.data(), y.empty() ? nullptr : y.data(), first_index));
+}
+
+// ---------------------------------------------------------------------------------------------------------------------
 // render(): main.cpp:169-266. Every literal of the reference is a field with the reference's value as default.
 struct RenderOptions {
     int width = 1024, height = 768;      // main.cpp:28-29

@@ -128,6 +128,13 @@ int cgrt_build_grid(cgrt_ctx *ctx);
 /* Photons with global indices [first, first+count) (main.cpp:231-247): emit, bounce, deposit into the per-round
  * accumulators. Index k always draws the same Philox stream, whichever GPU traces it. */
 int cgrt_photon_pass(cgrt_ctx *ctx, uint64_t first, uint64_t count);
+/* trace() itself (main.cpp:42) for n caller-made rays: org, dir, weight are n x 3 host doubles; depth is the recursion depth the rays start at.
+ * flag != 0, an eye ray (main.cpp:209): weight = adj, (x[i], y[i]) = the pixel (column, row) its hitpoints belong to; hitpoints are appended
+ *   exactly as cgrt_eye_pass appends them (call before cgrt_build_grid; rays of one call that share a pixel take sample numbers k mod samples).
+ * flag == 0, a photon (main.cpp:246): weight = flux; its diffuse hits deposit into the per-round accumulators like cgrt_photon_pass's (call
+ *   after cgrt_build_grid; x, y unused). Ray k draws the random numbers of photon index first_index + k (bounce = depth onwards). */
+int cgrt_trace(cgrt_ctx *ctx, int64_t n, const double *org, const double *dir, const double *weight, int flag, int depth,
+               const int32_t *x, const int32_t *y, uint64_t first_index);
 /* Device view of the per-round accumulators {dflux[3], m} (4 x fp64 per hitpoint, canonical order) for the all-reduce. */
 int cgrt_accum_dev(cgrt_ctx *ctx, void **ptr_dev, int64_t *n_doubles);
 /* ---- multi-GPU: NCCL is bound at run time (the copy already loaded in the process, else libnccl.so.2); none of
