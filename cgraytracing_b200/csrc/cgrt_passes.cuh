@@ -966,12 +966,14 @@ __global__ void __launch_bounds__(CGRT_DEPOSIT_BLOCK, CGRT_DEPOSIT_MINB) photon_
                             if (c < total) {
                                 hidx = b_lo + (c - e_lo);
                                 q = __ldg(pre + hidx);
-                                q_n = __ldg(pre_n + hidx);
-                                if (ACC == 1) q_f = __ldg(pre_f + hidx);
                                 const float ex = fmaxf(fmaxf(bx0 - bm - q.x, q.x - (bx0 + bw + bm)), 0.f);
                                 const float ey = fmaxf(fmaxf(by0 - bm - q.y, q.y - (by0 + bw + bm)), 0.f);
                                 const float ez = fmaxf(fmaxf(bz0 - bm - q.z, q.z - (bz0 + bw + bm)), 0.f);
                                 keep = fmaf(ez, ez, fmaf(ey, ey, ex * ex)) <= q.w;
+                                if (keep) {  // the other two filter records only for candidates that survive the cull (c5: deposit 89 -> 84 ms)
+                                    q_n = __ldg(pre_n + hidx);
+                                    if (ACC == 1) q_f = __ldg(pre_f + hidx);
+                                }
                             }
                             const unsigned int km = __ballot_sync(0xffffffffu, keep);
                             if (keep) {
