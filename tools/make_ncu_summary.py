@@ -6,7 +6,7 @@ here = os.path.dirname(os.path.abspath(__file__))
 run = lambda *a: subprocess.run(a, capture_output=True, text=True).stdout
 b = json.load(open(benchf))
 k = b["kernels"]
-sp = k["photon_trace_kernel"]["split_ms"]
+sp = k["photon_trace_family"]["split_ms"]
 out = []
 out.append(f"# {tag} - ncu evidence, one B200, {b['config']['workload']} {b['config']['width']}x{b['config']['height']}, "
            f"{b['config']['photons_per_gpu_per_step']} photons per round\n")
@@ -33,16 +33,17 @@ for name in ("photon_deposit", "photon_traverse", "photon_trace"):
     out.append(f"### {name}\n```\n{src}```\n")
 out.append("""## 5. Reading
 
-* No kernel is bound by HBM (DRAM throughput <= 35 % of the measured copy peak) or by launch overhead (16 launches per ~20 ms round).
+* No kernel is bound by HBM (DRAM throughput <= 35 % of the measured copy peak) or by launch overhead (16 launches per ~19 ms round).
 * photon_trace_kernel (emission and continuation) is bound by dependent fp64 latency: 4 warps per scheduler (114 registers), ~0.48 issue
-  slots per cycle, warp states `wait` + `short_scoreboard` + `long_scoreboard` ~ 65 %. Measured and found flat: block size 64/96/128,
-  register caps of 96/80/64. Kept: three plane quotients in flight, work drawn from the head of the index range, float root-box test.
-* photon_traverse_kernel is bound by divergence: 6-9 of 32 lanes live per instruction (one ray per lane, path lengths from 1 to hundreds
-  of nodes; the fp64 triangle test runs at 1.7 lanes). Restructurings that raise the live-lane count (while-while, per-lane refill,
-  postponed leaf batches) and a float triangle pretest were measured slower; dropping all fp64 box arithmetic was kept (-9 %).
-* photon_deposit_kernel is bound by the L1 / shared-memory pipe (l1tex ~ 90 %, ~0.59 issue slots per cycle, 28 of 32 lanes live): the
-  prefilter scan over the staged candidates and the drain into the pair queue are shared-memory traffic; the fp64 exact test left the
-  profile when pairs started being decided in fp32 from shared memory (`deposit_pair`).
+  slots per cycle, warp states `wait` + `short_scoreboard` + `long_scoreboard` ~ 65 %. Removing instructions does not move it (r02: axis-aligned
+  plane quotients without the dot products and a division-free texel index, both bit-exact: 4.78 vs 4.77 ms); neither do register caps of
+  96/80/64 or block sizes 64/96/128 (r01).
+* photon_traverse_kernel walks a 4-wide tree (r02): 7-9 of 32 lanes live per instruction (one ray per lane, path lengths from 1 to hundreds of
+  boxes), `long_scoreboard` ~ 50 %: dependent node and triangle fetches at 8 warps per scheduler. It is sensitive to every L1 transaction
+  (three unconditional stack stores per node: +11 %) and to occupancy (80 registers: +35 %), not to instruction count (fused slabs: flat).
+* photon_deposit_kernel is bound by the LSU data pipe (`l1tex__data_pipe_lsu_wavefronts` ~ 92 % of peak: half shared-memory loads — the
+  broadcast prefilter scan costs four wavefronts per staged candidate —, the rest record gathers, staging loads and one `red` per deposit).
+  r02 removed per-group work (a cell's staged list is reused by the following batches; filter records only for culled survivors).
 """)
 
 open(f"profiles/{tag}_ncu_summary.md", "w").write("\n".join(out))
