@@ -1610,8 +1610,12 @@ int cgrt_round_update(cgrt_ctx *ctx) {
     CKS(join_update(ctx));
     PhaseTimer timer(ctx, 4, ctx->profiling != 0);  // asynchronous unless profiling
     unsigned int n = ctx->nhp;
-    // the tail of a round on its own stream (see cgrt_ctx::ustream); on the main stream while profiling so that its events bracket it
-    cudaStream_t U = ctx->profiling ? ctx->stream : ctx->ustream;
+    // the tail of a round on its own stream (see cgrt_ctx::ustream); on the main stream while profiling so that its events bracket it —
+    // and when an NCCL all-reduce is part of it: measured on 8 GPUs, the collective on the side stream is SLOWER than in stream order
+    // (c2: 5.40 vs 4.93 ms per round, c1: 5.72 vs 5.54): NCCL's blocks cannot become resident next to the persistent emission kernel of
+    // the next round (4 blocks x 114 registers fill an SM), so the all-reduce starts late on some rank and every rank waits for it
+    static const bool comm_side = getenv("CGRT_COMM_SIDE_STREAM") != nullptr;  // dev: the side-stream variant
+    cudaStream_t U = (ctx->profiling || (ctx->comm && !comm_side)) ? ctx->stream : ctx->ustream;
     if (U != ctx->stream) {
         CK(cudaEventRecord(ctx->ev_tail, ctx->stream));
         CK(cudaStreamWaitEvent(U, ctx->ev_tail, 0));

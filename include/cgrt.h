@@ -148,9 +148,9 @@ int cgrt_comm_destroy(void *comm);
 /* Tile-sharded eye pass: all-gather the hitpoint records of every rank's rows (after cgrt_eye_pass(y0,y1), before cgrt_build_grid);
  * every rank then builds the same grid from the union. */
 int cgrt_allgather_hitpoints(cgrt_ctx *ctx, void *nccl_comm, int world);
-/* Attach a communicator: from now on cgrt_round_update all-reduces the accumulators {dflux.xyz, m} over it before applying the update.
- * The all-reduce and the update run on a side stream of the ctx and are only waited for by the NEXT round's gather, so the next round's
- * emission and traversal launches run underneath the collective. NULL detaches. */
+/* Attach a communicator: from now on cgrt_round_update all-reduces the accumulators {dflux.xyz, m} over it, in stream order, before
+ * applying the update (the variant that ran the collective on a side stream underneath the next round's trace launches was measured
+ * slower on 8 GPUs: NCCL's blocks do not fit next to the persistent trace kernels). NULL detaches. */
 int cgrt_set_comm(cgrt_ctx *ctx, void *nccl_comm, int world);
 /* All-reduce the accumulators now, on the ctx stream, asynchronously (NULL: single GPU, no-op). For hosts that drive the collective
  * themselves; with cgrt_set_comm it is implied by cgrt_round_update. */
