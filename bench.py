@@ -298,8 +298,9 @@ def run_gpu(args):
     t_commit = time.time() - t0
     # N > 1: both collectives of the path (all-gather of the eye tiles' hitpoint records, all-reduce of the accumulators) run inside the
     # library over its own NCCL communicator; --collective torch leaves the all-reduce to torch.distributed on the library's stream
-    comm = make_native_comm(local, rank, world) if (world > 1 and args.collective == "native") else None
-    eng = GpuEngine(g, local, comm, world)
+    comm = make_native_comm(local, rank, world) if (world > 1 and args.collective in ("native", "peer")) else None
+    peer = args.collective == "peer"
+    eng = GpuEngine(g, local, comm, world, rank=rank, peer=peer)
     R = ShardedRenderer(eng, rank, world)
     R.eye(HEIGHT)
     g.synchronize()
@@ -406,7 +407,7 @@ def run_gpu(args):
             with Context(local) as ge:
                 ge.set_config(cfg, accum_mode=args.accum)
                 scene.build_into(ge); ge.commit()
-                Re = ShardedRenderer(GpuEngine(ge, local, comm, world), rank, world)
+                Re = ShardedRenderer(GpuEngine(ge, local, comm, world, rank=rank, peer=peer), rank, world)
                 Re.eye(HEIGHT)
                 for _ in range(rounds):
                     Re.round(world * P)
@@ -423,6 +424,8 @@ def run_gpu(args):
                        f"eye pass (image rows sharded over the ranks, hitpoint records all-gathered) + grid + {args.e2e_rounds} rounds x "
                        f"{world * P} photons + all-reduce + updates + fp64 image and 8-bit image download on every rank, wall clock, max over ranks"}
 
+    photon_chunk = g.photon_chunk()
+    g.close()  # every rank at the same point: with the peer exchange a context's shutdown is a handshake between the ranks
     if rank != 0:
         if world > 1:
             dist.destroy_process_group()
@@ -438,7 +441,7 @@ def run_gpu(args):
     dt = lambda k: (tp1[k] - tp0[k]) * 1e-3
     t_trace, t_dep, t_upd, t_sort = dt("photon_trace"), dt("photon_deposit"), dt("update"), dt("deposit_sort")
     t_emit, t_trav, t_cont = dt("trace_emit"), dt("trace_traverse"), dt("trace_continue")
-    n_chunks = (P + g.photon_chunk() - 1) // max(1, g.photon_chunk())
+    n_chunks = (P + photon_chunk - 1) // max(1, photon_chunk)
     rec_b = deposit_record_bytes()
     # (1) SURVEY 8(d): bytes the REFERENCE's algorithm touches for the same work, in device-layout record sizes
     bytes_trace = seg * (B_SEGMENT + B_NODE * per_seg_nodes + B_TRI * per_seg_tris)
@@ -536,8 +539,10 @@ def main():
     ap.add_argument("--cpu-photons", type=int, default=400000, help="photon budget of the CPU baseline sample (0 = skip)")
     ap.add_argument("--ref-photons", type=int, default=200000, help="photons per step of --impl reference")
     ap.add_argument("--shipped-photons", type=int, default=100000, help="total photons of the 'reference as shipped' leg (oracle/_ref; 0 = skip)")
-    ap.add_argument("--collective", default="native", choices=["native", "torch"], help="N > 1: all-reduce inside the library (own NCCL communicator, "
-                    "overlapped with the next round's trace) or by torch.distributed on the library's stream")
+    ap.add_argument("--collective", default="peer", choices=["peer", "native", "torch"],
+                    help="N > 1: how the accumulators of a round are exchanged. peer: over peer memory inside the library, fused with the update and "
+                         "overlapped with the next round's trace (no collective call in a round); native: ncclAllReduce inside the library, in stream "
+                         "order; torch: torch.distributed all-reduce on the library's stream")
     ap.add_argument("--f64-too", type=int, default=1, help="1: also time the same rounds with fp64 accumulators (value_f64_accumulators)")
     ap.add_argument("--e2e-rounds", type=int, default=-1, help="rounds of the end-to-end render() (default: the workload's own, c3 = 50; 0 = skip)")
     args = ap.parse_args()

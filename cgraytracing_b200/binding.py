@@ -28,7 +28,7 @@ ABI_SYMBOLS = [
     "cgrt_accum_dev", "cgrt_allreduce_accum", "cgrt_round_update", "cgrt_gather_image", "cgrt_num_hitpoints", "cgrt_download_hitpoints",
     "cgrt_download_accum", "cgrt_download_grid", "cgrt_get_counters", "cgrt_get_timings", "cgrt_set_counting", "cgrt_set_profiling", "cgrt_set_culling", "cgrt_set_overlap", "cgrt_average_u8", "cgrt_average_f64",
     "cgrt_check_guards", "cgrt_release_cached_memory", "cgrt_photon_chunk", "cgrt_deposit_record_bytes", "cgrt_trace",
-    "cgrt_comm_unique_id", "cgrt_comm_init_rank", "cgrt_comm_init_all", "cgrt_comm_destroy", "cgrt_allgather_hitpoints", "cgrt_set_comm",
+    "cgrt_peer_export", "cgrt_peer_attach", "cgrt_comm_unique_id", "cgrt_comm_init_rank", "cgrt_comm_init_all", "cgrt_comm_destroy", "cgrt_allgather_hitpoints", "cgrt_set_comm",
 ]
 
 
@@ -352,6 +352,18 @@ class Context:
 
     def allreduce_accum(self, comm):
         self._ck(self.L.cgrt_allreduce_accum(self.h, C.c_void_p(comm)))
+
+    def peer_export(self) -> bytes:
+        """This rank's 128-byte handle of its accumulator block (after build_grid); see cgrt_peer_export."""
+        buf = C.create_string_buffer(128)
+        self._ck(self.L.cgrt_peer_export(self.h, buf))
+        return buf.raw
+
+    def peer_attach(self, rank: int, world: int, handles) -> None:
+        """handles: the `world` blobs of peer_export in rank order. From now on round_update exchanges over peer memory."""
+        blob = b"".join(handles)
+        assert len(blob) == 128 * world
+        self._ck(self.L.cgrt_peer_attach(self.h, int(rank), int(world), blob))
 
     def set_profiling(self, on=True):
         self._ck(self.L.cgrt_set_profiling(self.h, int(on)))

@@ -2,6 +2,8 @@
 // There is NO CPU fallback anywhere in this file: without a CUDA device cgrt_create fails with CGRT_ERR_NO_DEVICE.
 #include "../../include/cgrt.h"
 
+#include <unistd.h>
+
 #include <cmath>
 #include <cstdio>
 #include <cstdlib>
@@ -220,6 +222,17 @@ struct cgrt_ctx {
     bool update_pending = false;
     void *comm = nullptr;   // ncclComm_t attached by cgrt_set_comm (not owned)
     int comm_world = 1;
+    // peer-memory exchange (cgrt_peer_export / cgrt_peer_attach): this rank's shared block = two accumulator buffers (round parity), flag
+    // arrays for rounds and for shutdown, an error word; and the mapped blocks of the other ranks
+    struct Peer {
+        char *block = nullptr;          // own block (cudaMalloc)
+        size_t acc_bytes = 0, bytes = 0;
+        int rank = -1, world = 0;
+        int round = 0, parity = 0;
+        bool attached = false;
+        char *base[CGRT_MAX_PEERS] = {};    // every rank's block as mapped here (own included)
+        bool ipc[CGRT_MAX_PEERS] = {};      // opened with cudaIpcOpenMemHandle (to be closed)
+    } peer;
     int sm_count = 148;
     int overlap = 0;  // measured on c3: the two halves slow each other down by more than they overlap (25.3 vs 24.2 ms per round)
     // resident-grid sizes of the persistent photon kernels (SMs x occupancy), so that static striding leaves no tail of late blocks
@@ -679,6 +692,42 @@ int download_free(cgrt_ctx *ctx, T *h, T *d, size_t n) {
 }
 }  // namespace
 
+// ---- peer-memory exchange -------------------------------------------------------------------------------------------------------------
+namespace {
+struct PeerBlob {  // CGRT_PEER_HANDLE_BYTES = 128
+    cudaIpcMemHandle_t handle;  // 64 bytes
+    uint64_t pid, ptr, bytes, acc_bytes;
+    int32_t device, nhp, accum_mode, magic;
+    char pad[128 - 64 - 4 * 8 - 4 * 4];
+};
+static_assert(sizeof(PeerBlob) == 128, "peer handle blob is 128 bytes");
+inline size_t peer_flags_off(const cgrt_ctx::Peer &p) { return 2 * p.acc_bytes; }                                   // int[CGRT_MAX_PEERS]: rounds
+inline size_t peer_done_off(const cgrt_ctx::Peer &p) { return 2 * p.acc_bytes + CGRT_MAX_PEERS * sizeof(int); }      // int[CGRT_MAX_PEERS]: shutdown
+inline size_t peer_err_off(const cgrt_ctx::Peer &p) { return 2 * p.acc_bytes + 2 * CGRT_MAX_PEERS * sizeof(int); }   // int
+const unsigned long long PEER_TIMEOUT_NS = 20ull * 1000 * 1000 * 1000;
+
+// Shutdown handshake + unmapping (cgrt_destroy): a rank may only free its block when no peer can still be reading it.
+void peer_release(cgrt_ctx *ctx) {
+    cgrt_ctx::Peer &P = ctx->peer;
+    if (!P.block) return;
+    cudaSetDevice(ctx->device);
+    if (ctx->ustream) cudaStreamSynchronize(ctx->ustream);
+    cudaStreamSynchronize(ctx->stream);
+    if (P.attached) {
+        PeerPtrs done;
+        for (int g = 0; g < CGRT_MAX_PEERS; g++) done.p[g] = g < P.world ? P.base[g] + peer_done_off(P) : nullptr;
+        peer_signal_kernel<<<1, 32, 0, ctx->stream>>>(done, P.rank, P.world, 1);
+        peer_wait_kernel<<<1, 32, 0, ctx->stream>>>(reinterpret_cast<const int *>(P.block + peer_done_off(P)), P.world, 1, PEER_TIMEOUT_NS,
+                                                  reinterpret_cast<int *>(P.block + peer_err_off(P)));
+        cudaStreamSynchronize(ctx->stream);
+        for (int g = 0; g < P.world; g++)
+            if (P.ipc[g]) cudaIpcCloseMemHandle(P.base[g]);
+    }
+    cudaFree(P.block);
+    P = cgrt_ctx::Peer();
+}
+}  // namespace
+
 // =================================================================================================================
 extern "C" {
 
@@ -763,6 +812,7 @@ int cgrt_destroy(cgrt_ctx *ctx) {
     if (ctx->tstream) cudaStreamSynchronize(ctx->tstream);
     if (ctx->ustream) cudaStreamSynchronize(ctx->ustream);
     cudaStreamSynchronize(ctx->stream);
+    peer_release(ctx);  // shutdown handshake with the other ranks, unmap their blocks, free ours
     for (auto &b : ctx->dep) {
         if (b.traced) cudaEventDestroy(b.traced);
         if (b.drained) cudaEventDestroy(b.drained);
@@ -819,6 +869,11 @@ int cgrt_synchronize(cgrt_ctx *ctx) {
     CK(cudaStreamSynchronize(ctx->tstream));
     CKS(join_update(ctx));
     CK(cudaStreamSynchronize(ctx->stream));
+    if (ctx->peer.attached) {  // did a wait for the other ranks give up?
+        int perr = 0;
+        CK(cudaMemcpy(&perr, ctx->peer.block + peer_err_off(ctx->peer), sizeof perr, cudaMemcpyDeviceToHost));
+        if (perr) FAIL(CGRT_ERR_NCCL, "peer exchange: rank " + std::to_string(perr - 1) + " did not publish its round in time");
+    }
     if (!ctx->timeline.empty()) {
         for (size_t k = 0; k + 3 < ctx->timeline.size(); k += 4) {
             float t[4];
@@ -1518,6 +1573,72 @@ int cgrt_allreduce_accum(cgrt_ctx *ctx, void *nccl_comm) {
     return allreduce_on(ctx, nccl_comm, ctx->stream);  // asynchronous, ordered on the ctx stream
 }
 
+
+int cgrt_peer_export(cgrt_ctx *ctx, void *handle128) {
+    if (!ctx || !handle128) return CGRT_ERR_INVALID;
+    if (!ctx->grid_built) FAIL(CGRT_ERR_INVALID, "build the grid first");
+    if (ctx->cfg.update_mode == 0) FAIL(CGRT_ERR_INVALID, "the per-photon update is not shard-invariant (one GPU only)");
+    if (ctx->peer.block) FAIL(CGRT_ERR_INVALID, "peer block already exported");
+    CK(cudaSetDevice(ctx->device));
+    CKS(join_update(ctx));
+    CK(cudaStreamSynchronize(ctx->stream));
+    cgrt_ctx::Peer &P = ctx->peer;
+    const size_t elem = ctx->cfg.accum_mode == 0 ? sizeof(double) : sizeof(float);
+    P.acc_bytes = (((size_t)ctx->nhp * 4 * elem) + 255) & ~(size_t)255;
+    if (P.acc_bytes == 0) P.acc_bytes = 256;
+    P.bytes = 2 * P.acc_bytes + 2 * CGRT_MAX_PEERS * sizeof(int) + 256;
+    // a plain cudaMalloc block: pool (cudaMallocAsync) memory cannot be exported
+    if (cudaMalloc(&P.block, P.bytes) != cudaSuccess) { P = cgrt_ctx::Peer(); cudaGetLastError(); FAIL(CGRT_ERR_CUDA, "out of device memory for the peer block"); }
+    CK(cudaMemset(P.block, 0, P.bytes));
+    // carry over what has been accumulated so far (normally nothing)
+    CK(cudaMemcpy(P.block, ctx->acc, (size_t)ctx->nhp * 4 * elem, cudaMemcpyDeviceToDevice));
+    ctx->acc = P.block;
+    PeerBlob b;
+    memset(&b, 0, sizeof b);
+    CK(cudaIpcGetMemHandle(&b.handle, P.block));
+    b.pid = (uint64_t)getpid(); b.ptr = (uint64_t)(uintptr_t)P.block; b.bytes = P.bytes; b.acc_bytes = P.acc_bytes;
+    b.device = ctx->device; b.nhp = (int32_t)ctx->nhp; b.accum_mode = ctx->cfg.accum_mode; b.magic = 0x43475250;
+    memcpy(handle128, &b, sizeof b);
+    return CGRT_OK;
+}
+
+int cgrt_peer_attach(cgrt_ctx *ctx, int rank, int world, const void *handles) {
+    if (!ctx || !handles || world < 1 || world > CGRT_MAX_PEERS || rank < 0 || rank >= world) return CGRT_ERR_INVALID;
+    cgrt_ctx::Peer &P = ctx->peer;
+    if (!P.block) FAIL(CGRT_ERR_INVALID, "cgrt_peer_export first");
+    if (P.attached) FAIL(CGRT_ERR_INVALID, "peers already attached");
+    CK(cudaSetDevice(ctx->device));
+    const PeerBlob *B = reinterpret_cast<const PeerBlob *>(handles);
+    for (int g = 0; g < world; g++) {
+        if (B[g].magic != 0x43475250) FAIL(CGRT_ERR_INVALID, "not a peer handle");
+        if (B[g].nhp != (int32_t)ctx->nhp || B[g].accum_mode != ctx->cfg.accum_mode || B[g].acc_bytes != P.acc_bytes)
+            FAIL(CGRT_ERR_INVALID, "peer " + std::to_string(g) + " holds a different hitpoint set or accumulator type");
+    }
+    if (B[rank].ptr != (uint64_t)(uintptr_t)P.block) FAIL(CGRT_ERR_INVALID, "handles[rank] is not this context's own handle");
+    for (int g = 0; g < world; g++) {
+        if (g == rank) { P.base[g] = P.block; continue; }
+        if (B[g].pid == (uint64_t)getpid()) {  // another context of this process: peer access, the pointer is valid as it is
+            if (B[g].device != ctx->device) {
+                int can = 0;
+                CK(cudaDeviceCanAccessPeer(&can, ctx->device, B[g].device));
+                if (!can) FAIL(CGRT_ERR_CUDA, "no peer access between devices " + std::to_string(ctx->device) + " and " + std::to_string(B[g].device));
+                cudaError_t e = cudaDeviceEnablePeerAccess(B[g].device, 0);
+                if (e != cudaSuccess && e != cudaErrorPeerAccessAlreadyEnabled) { cudaGetLastError(); FAIL(CGRT_ERR_CUDA, "cudaDeviceEnablePeerAccess failed"); }
+                cudaGetLastError();
+            }
+            P.base[g] = reinterpret_cast<char *>((uintptr_t)B[g].ptr);
+        } else {
+            void *q = nullptr;
+            cudaError_t e = cudaIpcOpenMemHandle(&q, B[g].handle, cudaIpcMemLazyEnablePeerAccess);
+            if (e != cudaSuccess) { cudaGetLastError(); FAIL(CGRT_ERR_CUDA, std::string("cudaIpcOpenMemHandle: ") + cudaGetErrorString(e)); }
+            P.base[g] = reinterpret_cast<char *>(q);
+            P.ipc[g] = true;
+        }
+    }
+    P.rank = rank; P.world = world; P.round = 0; P.parity = 0; P.attached = true;
+    return CGRT_OK;
+}
+
 int cgrt_set_comm(cgrt_ctx *ctx, void *nccl_comm, int world) {
     if (!ctx || world < 1) return CGRT_ERR_INVALID;
     if (nccl_comm && ctx->cfg.update_mode == 0) FAIL(CGRT_ERR_INVALID, "the per-photon update is not shard-invariant (one GPU only)");
@@ -1619,6 +1740,35 @@ int cgrt_round_update(cgrt_ctx *ctx) {
     if (U != ctx->stream) {
         CK(cudaEventRecord(ctx->ev_tail, ctx->stream));
         CK(cudaStreamWaitEvent(U, ctx->ev_tail, 0));
+    }
+    if (ctx->peer.attached) {
+        // the exchange over peer memory fused with the update (see peer_reduce_update_kernel); always on the side stream
+        cgrt_ctx::Peer &P = ctx->peer;
+        timer.stop();
+        const int value = ++P.round;
+        PeerPtrs flags, accs;
+        for (int g = 0; g < CGRT_MAX_PEERS; g++) {
+            flags.p[g] = g < P.world ? P.base[g] + peer_flags_off(P) : nullptr;
+            accs.p[g] = g < P.world ? P.base[g] + (size_t)P.parity * P.acc_bytes : nullptr;
+        }
+        peer_signal_kernel<<<1, 32, 0, ctx->stream>>>(flags, P.rank, P.world, value);
+        cudaStream_t V = ctx->ustream;
+        CK(cudaEventRecord(ctx->ev_tail, ctx->stream));
+        CK(cudaStreamWaitEvent(V, ctx->ev_tail, 0));
+        peer_wait_kernel<<<1, 32, 0, V>>>(reinterpret_cast<const int *>(P.block + peer_flags_off(P)), P.world, value, PEER_TIMEOUT_NS,
+                                         reinterpret_cast<int *>(P.block + peer_err_off(P)));
+        void *clear_next = P.block + (size_t)(P.parity ^ 1) * P.acc_bytes;
+        if (n > 0) {
+            if (ctx->cfg.accum_mode == 0) peer_reduce_update_kernel<0><<<nblk(n, 128), 128, 0, V>>>(n, ctx->P.alpha, ctx->A, accs, P.world, clear_next);
+            else peer_reduce_update_kernel<1><<<nblk(n, 128), 128, 0, V>>>(n, ctx->P.alpha, ctx->A, accs, P.world, clear_next);
+        }
+        ctx->launches += 3;
+        CK(cudaGetLastError());
+        CK(cudaEventRecord(ctx->ev_updated, V));
+        ctx->update_pending = true;
+        P.parity ^= 1;
+        ctx->acc = P.block + (size_t)P.parity * P.acc_bytes;  // the next round deposits into the other buffer
+        return CGRT_OK;
     }
     if (ctx->comm) CKS(allreduce_on(ctx, ctx->comm, U));
     if (n > 0 && ctx->cfg.update_mode == 0) {

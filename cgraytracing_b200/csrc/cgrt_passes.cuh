@@ -1158,6 +1158,86 @@ __global__ void round_update_kernel(unsigned int n, double alpha, HpArrays A, vo
     }
 }
 
+// =================================================================================================================
+// The round's exchange over peer memory (one box, NVLink / NVSwitch) fused with the update: no collective library call in the round.
+// Every rank keeps its accumulators in a cudaMalloc block that all ranks have mapped (CUDA IPC between processes, peer access inside one
+// process). After its deposit kernel a rank publishes "round r deposited" in every peer's flag array; on a side stream a one-block
+// kernel waits until all ranks have published r, then ONE kernel reads every rank's accumulators straight out of their memory (P2P
+// loads, ranks summed in rank order so that every rank gets the same bits), applies the round update to its own replica of the
+// hitpoints and clears its own accumulators of the round after. The accumulators are double-buffered by round parity: a buffer is only
+// written again two rounds later, and a rank that has published round r has finished reading round r-1 everywhere (its update r-1
+// precedes its deposit r), so no second handshake is needed. Only the NEXT round's deposit kernel waits for this — the next round's
+// emission and traversal run underneath, which also absorbs the skew between ranks that a synchronous all-reduce pays every round.
+// =================================================================================================================
+#define CGRT_MAX_PEERS 16
+struct PeerPtrs {
+    void *p[CGRT_MAX_PEERS];
+};
+__device__ __forceinline__ void st_release_sys(int *p, int v) { asm volatile("st.release.sys.global.s32 [%0], %1;" ::"l"(p), "r"(v) : "memory"); }
+__device__ __forceinline__ int ld_acquire_sys(const int *p) {
+    int v;
+    asm volatile("ld.acquire.sys.global.s32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+    return v;
+}
+// flags.p[g] = rank g's flag array (world ints); this rank writes its own slot in each of them
+__global__ void peer_signal_kernel(PeerPtrs flags, int rank, int world, int value) {
+    const int g = threadIdx.x;
+    if (g < world) {
+        __threadfence_system();
+        st_release_sys(reinterpret_cast<int *>(flags.p[g]) + rank, value);
+    }
+}
+// waits until every slot of this rank's own flag array has reached `value`; gives up after `timeout_ns` and raises *err (never hangs the GPU)
+__global__ void peer_wait_kernel(const int *my_flags, int world, int value, unsigned long long timeout_ns, int *err) {
+    const int g = threadIdx.x;
+    if (g >= world) return;
+    unsigned long long t0, t;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t0));
+    while (ld_acquire_sys(my_flags + g) < value) {
+        __nanosleep(200);
+        asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+        if (t - t0 > timeout_ns) { atomicExch(err, 1 + g); return; }
+    }
+}
+// acc.p[g] = rank g's accumulators of this round's parity; clear_next = this rank's accumulators of the other parity
+template <int ACC>
+__global__ void __launch_bounds__(128) peer_reduce_update_kernel(unsigned int n, double alpha, HpArrays A, PeerPtrs acc, int world, void *__restrict__ clear_next) {
+    unsigned int k = blockIdx.x * blockDim.x + threadIdx.x;
+    if (k >= n) return;
+    double dx = 0, dy = 0, dz = 0, m = 0;
+    if (ACC == 0) {
+        for (int g = 0; g < world; g++) {
+            const double2 *ap = reinterpret_cast<const double2 *>(reinterpret_cast<const double4 *>(acc.p[g]) + k);
+            const double2 a0 = __ldcg(ap), a1 = __ldcg(ap + 1);
+            dx += a0.x; dy += a0.y; dz += a1.x; m += a1.y;
+        }
+        reinterpret_cast<double4 *>(clear_next)[k] = make_double4(0, 0, 0, 0);
+    } else {
+        float fx = 0, fy = 0, fz = 0, fm = 0;  // float sums in rank order: what an all-reduce of float accumulators produces, identical on every rank
+        for (int g = 0; g < world; g++) {
+            const float4 a = __ldcg(reinterpret_cast<const float4 *>(acc.p[g]) + k);
+            fx += a.x; fy += a.y; fz += a.z; fm += a.w;
+        }
+        dx = fx; dy = fy; dz = fz; m = fm;
+        reinterpret_cast<float4 *>(clear_next)[k] = make_float4(0, 0, 0, 0);
+    }
+    if (m > 0) {
+        int cnt = A.cnt[k];
+        double na = cnt * alpha;
+        double g = (na + alpha * m) / (na + m);
+        double *fl = A.flux + 4 * (size_t)k;
+        fl[0] = (fl[0] + dx) * g;
+        fl[1] = (fl[1] + dy) * g;
+        fl[2] = (fl[2] + dz) * g;
+        HpHot hh = A.hot[k];
+        hh.r2 *= g;
+        A.hot[k].r2 = hh.r2;
+        A.pre[k] = make_prefilter(hh.px, hh.py, hh.pz, hh.r2);
+        A.pre_n[k].w = prefilter_inner(hh.px, hh.py, hh.pz, hh.r2);
+        A.cnt[k] = cnt + (int)m;
+    }
+}
+
 // Per-photon update mode: the counts are live; a "round update" only folds them into what the next round's filters and the image read:
 // r2 = table[n], flux = S * r2 (see deposit_u1), filter radii. The sums S stay in the accumulator buffer for the whole render.
 __global__ void round_update_u1_kernel(unsigned int n, HpArrays A, const double *__restrict__ S, const double *__restrict__ r2tab, int cap, int *maxcnt) {

@@ -67,13 +67,16 @@ class GpuEngine:
     (cgrt_allgather_hitpoints; the all-reduce is part of cgrt_round_update and overlaps the next round's trace launches).
     Without it the host framework reduces the accumulator buffer itself (torch.distributed on the library's stream)."""
 
-    def __init__(self, ctx, device: int, comm=None, world: int = 1):
+    def __init__(self, ctx, device: int, comm=None, world: int = 1, rank: int = 0, peer: bool = False, group=None):
         import torch
 
         self.ctx, self.device, self.torch = ctx, device, torch
-        self.comm, self.world = comm, world
+        self.comm, self.world, self.rank, self.group = comm, world, rank, group
         self.native_collectives = comm is not None
-        if comm is not None:
+        # peer = True: the per-round exchange runs over peer memory inside the library (cgrt_peer_*): no collective call in a round,
+        # the reduction is fused with the update and overlaps the next round's trace. The communicator then only serves the eye tiles.
+        self.peer = bool(peer) and world > 1
+        if comm is not None and not self.peer:
             ctx.set_comm(comm, world)
         # collectives are enqueued relative to the library's own stream: no host synchronisation between the photon pass, the
         # all-reduce and the update
@@ -101,6 +104,13 @@ class GpuEngine:
 
     def build_grid(self):
         self.ctx.build_grid()
+        if self.peer:
+            import torch.distributed as dist
+
+            mine = self.ctx.peer_export()
+            blobs = [None] * self.world
+            dist.all_gather_object(blobs, mine, group=self.group)
+            self.ctx.peer_attach(self.rank, self.world, blobs)
         ptr, n = self.ctx.accum_dev()
         ts = "<f8" if self.ctx.accum_mode == 0 else "<f4"
         self._acc = self.torch.as_tensor(_DevArray(ptr, n, ts), device=f"cuda:{self.device}") if n else None
@@ -163,7 +173,7 @@ class ShardedRenderer:
         first, count = photon_shard(self.rounds_done, photons_per_round, self.rank, self.world)
         if count:
             self.e.photon_pass(first, count)
-        if self.world > 1 and not getattr(self.e, "native_collectives", False):
+        if self.world > 1 and not getattr(self.e, "native_collectives", False) and not getattr(self.e, "peer", False):
             import torch.distributed as dist
 
             import contextlib

@@ -22,11 +22,14 @@
 #include <cmath>
 #include <cstdint>
 #include <cstdio>
+#include <cstring>
 #include <fstream>
 #include <memory>
 #include <sstream>
 #include <stdexcept>
 #include <string>
+#include <condition_variable>
+#include <mutex>
 #include <thread>
 #include <vector>
 
@@ -308,6 +311,8 @@ struct RenderOptions {
                                          // (one GPU; `rounds` then only says how often filter radii are refreshed). false: one update per round
     uint64_t seed = 20261018ull;
     int device = 0;
+    bool peer_exchange = true;           // num_gpus > 1: exchange the accumulators of a round over peer memory, fused with the update
+                                         // (cgrt_peer_*); false: ncclAllReduce inside cgrt_round_update
     int num_gpus = 1;                    // > 1: devices device .. device+num_gpus-1 of this box, one context and one host thread per GPU:
                                          // image rows and photon index ranges are split between them, NCCL (through the C ABI) carries the
                                          // hitpoint records and the per-round accumulators
@@ -320,9 +325,29 @@ struct Image {
     Vec3 at(int h, int w) const { const double *p = &rgb[((size_t)h * width + w) * 3]; return Vec3(p[0], p[1], p[2]); }
 };
 
+// Where the ranks of one process (one host thread per GPU) hand each other their peer handles.
+struct PeerHub {
+    explicit PeerHub(int world) : blobs((size_t)world * CGRT_PEER_HANDLE_BYTES), world_(world) {}
+    // deposits this rank's handle, returns when every rank has (or one has failed)
+    bool exchange(int rank, const char *blob) {
+        std::unique_lock<std::mutex> lk(m);
+        if (blob) std::memcpy(&blobs[(size_t)rank * CGRT_PEER_HANDLE_BYTES], blob, CGRT_PEER_HANDLE_BYTES); else failed = true;
+        arrived++;
+        cv.notify_all();
+        cv.wait(lk, [&] { return arrived >= world_; });
+        return !failed;
+    }
+    std::vector<char> blobs;
+    std::mutex m;
+    std::condition_variable cv;
+    int arrived = 0, world_;
+    bool failed = false;
+};
+
 // One rank of render(): the whole of main.cpp:169-266 on one GPU for its share of the rows and of the photon indices. comm == nullptr:
 // the single-GPU render.
-inline Image render_rank(const std::vector<Object *> &objs, const RenderOptions &opt, int rank, int world, void *comm, cgrt_counters *counters) {
+inline Image render_rank(const std::vector<Object *> &objs, const RenderOptions &opt, int rank, int world, void *comm, cgrt_counters *counters,
+                         PeerHub *hub = nullptr) {
     Context c(opt.device + rank);
     cgrt_config cfg;
     cgrt_default_config(&cfg);
@@ -338,9 +363,17 @@ inline Image render_rank(const std::vector<Object *> &objs, const RenderOptions 
     if (y1 > y0) c.check(cgrt_eye_pass(c.get(), y0, y1));
     if (comm) {
         c.check(cgrt_allgather_hitpoints(c.get(), comm, world));
-        c.check(cgrt_set_comm(c.get(), comm, world));  // cgrt_round_update all-reduces the accumulators from now on
+        if (!hub) c.check(cgrt_set_comm(c.get(), comm, world));  // cgrt_round_update all-reduces the accumulators from now on
     }
     c.check(cgrt_build_grid(c.get()));                // hash.h:43-54 as a sorted grid
+    if (hub) {  // the accumulators of a round are exchanged over peer memory, fused with the update
+        char blob[CGRT_PEER_HANDLE_BYTES];
+        int st = cgrt_peer_export(c.get(), blob);
+        bool ok = hub->exchange(rank, st == CGRT_OK ? blob : nullptr);
+        c.check(st);
+        if (!ok) throw Error(CGRT_ERR_CUDA, "a peer rank failed to export its accumulator block");
+        c.check(cgrt_peer_attach(c.get(), rank, world, hub->blobs.data()));
+    }
     const uint64_t total = (uint64_t)opt.num_photon * (uint64_t)opt.num_threads;
     const int rounds = opt.rounds < 1 ? 1 : opt.rounds;
     uint64_t done = 0;
@@ -375,10 +408,11 @@ inline Image render(const std::vector<Object *> &objs, const RenderOptions &opt 
     std::vector<cgrt_counters> ctrs((size_t)world);
     std::vector<std::string> errs((size_t)world);
     std::vector<int> stat((size_t)world, 0);
+    PeerHub hub(world);
     std::vector<std::thread> th;
     for (int k = 0; k < world; k++)
         th.emplace_back([&, k] {
-            try { imgs[(size_t)k] = render_rank(objs, opt, k, world, comms[(size_t)k], &ctrs[(size_t)k]); }
+            try { imgs[(size_t)k] = render_rank(objs, opt, k, world, comms[(size_t)k], &ctrs[(size_t)k], opt.peer_exchange ? &hub : nullptr); }
             catch (const Error &e) { stat[(size_t)k] = e.status ? e.status : CGRT_ERR_CUDA; errs[(size_t)k] = e.what(); }
         });
     for (auto &t : th) t.join();

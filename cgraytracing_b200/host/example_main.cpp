@@ -1,7 +1,7 @@
 // example_main.cpp — what the reference's main() (main.cpp:268-414) looks like on top of cgrt_host.hpp: build the scene
 // objects on the stack, push raw Object* into a vector, call render(objs) once, tone-map and write the picture.
 //
-//   example_main <scene> <width> <height> <photons> <rounds> <out.ppm> [assets-dir] [gpus]
+//   example_main <scene> <width> <height> <photons> <rounds> <out.ppm> [assets-dir] [gpus] [peer|nccl]
 //   scenes: bunny (main.cpp:293 + chessboard floor), dragon (glass dragon, BASELINE config 3), spheres (main.cpp:288-290)
 //
 // Prints one line: "<hitpoints> <deposits> <fnv1a-64 of the fp64 image> <mean 8-bit level>" — tests/test_gpu_host_cpp.py
@@ -16,7 +16,7 @@ using namespace cgrt_host;
 
 int main(int argc, char **argv) {
     if (argc < 7) {
-        std::fprintf(stderr, "usage: %s <bunny|dragon|spheres> <width> <height> <photons> <rounds> <out.ppm> [assets-dir] [gpus]\n", argv[0]);
+        std::fprintf(stderr, "usage: %s <bunny|dragon|spheres> <width> <height> <photons> <rounds> <out.ppm> [assets-dir] [gpus] [peer|nccl]\n", argv[0]);
         return 2;
     }
     const std::string scene = argv[1], out = argv[6], assets = argc > 7 ? argv[7] : "cgraytracing_b200/assets";
@@ -24,6 +24,7 @@ int main(int argc, char **argv) {
     opt.width = std::atoi(argv[2]); opt.height = std::atoi(argv[3]);
     opt.num_photon = std::atoi(argv[4]); opt.num_threads = 1; opt.rounds = std::atoi(argv[5]);
     opt.num_gpus = argc > 8 ? std::atoi(argv[8]) : 1;  // > 1: rows and photon ranges split over that many GPUs of this box
+    opt.peer_exchange = !(argc > 9 && std::string(argv[9]) == "nccl");  // default: accumulators exchanged over peer memory
     try {
         // floor texture: Texture(tdata, Vec3(0,1,0), Vec3(-21,0,0), 42, 40, false) — main.cpp:320 with ChessBoard.png
         int tw = 0, th = 0;

@@ -152,6 +152,17 @@ int cgrt_allgather_hitpoints(cgrt_ctx *ctx, void *nccl_comm, int world);
  * applying the update (the variant that ran the collective on a side stream underneath the next round's trace launches was measured
  * slower on 8 GPUs: NCCL's blocks do not fit next to the persistent trace kernels). NULL detaches. */
 int cgrt_set_comm(cgrt_ctx *ctx, void *nccl_comm, int world);
+/* The same exchange without a collective call, over peer memory (GPUs of one box, NVLink / NVSwitch): every rank's accumulators live in a
+ * block all ranks have mapped; cgrt_round_update publishes "round deposited" flags and ONE kernel on a side stream reads every rank's
+ * accumulators out of their memory, applies the update and clears the next round's buffer (double-buffered by round parity). Only the
+ * next round's deposit kernel waits for it: the next round's trace runs underneath, and the skew between ranks is absorbed instead of
+ * being paid every round. After cgrt_build_grid on every rank: export one 128-byte handle per rank, carry all of them to every rank
+ * (the launcher's job: torch.distributed, MPI, or shared memory between the threads of one process), attach. Ranks may be processes
+ * (CUDA IPC) or contexts of one process (peer access). A rank that does not arrive within 20 s raises an error on the others at the
+ * next cgrt_synchronize instead of hanging them; cgrt_destroy waits for the peers' last reads before it frees the block. */
+#define CGRT_PEER_HANDLE_BYTES 128
+int cgrt_peer_export(cgrt_ctx *ctx, void *handle128);
+int cgrt_peer_attach(cgrt_ctx *ctx, int rank, int world, const void *handles /* world x CGRT_PEER_HANDLE_BYTES, rank order */);
 /* All-reduce the accumulators now, on the ctx stream, asynchronously (NULL: single GPU, no-op). For hosts that drive the collective
  * themselves; with cgrt_set_comm it is implied by cgrt_round_update. */
 int cgrt_allreduce_accum(cgrt_ctx *ctx, void *nccl_comm);

@@ -90,10 +90,12 @@ def test_cpp_two_gpu_render_equals_one_gpu(host_bins, tmp_path):
     exe, _ = host_bins
     assets = os.path.join(ROOT, "cgraytracing_b200", "assets")
     outs = []
-    for gpus in (1, 2):
-        o = subprocess.check_output([exe, "bunny", "160", "120", "60001", "3", str(tmp_path / f"o{gpus}.ppm"), assets, str(gpus)], text=True)
+    for tag, gpus, how in (("1", 1, "peer"), ("2p", 2, "peer"), ("2n", 2, "nccl")):  # both exchanges: over peer memory (default) and ncclAllReduce
+        o = subprocess.check_output([exe, "bunny", "160", "120", "60001", "3", str(tmp_path / f"o{tag}.ppm"), assets, str(gpus), how], text=True)
         outs.append(o.strip().splitlines()[-1].split())  # the last line is the program's (NCCL prints its version banner on stdout first)
-    assert outs[0][0] == outs[1][0] and outs[0][1] == outs[1][1] and int(outs[0][1]) > 0   # hitpoints, deposits
-    a, b = (np.frombuffer((tmp_path / f"o{g}.ppm").read_bytes()[-160 * 120 * 3:], np.uint8) for g in (1, 2))
-    assert np.abs(a.astype(int) - b.astype(int)).max() <= 1   # fp64 atomics + all-reduce order: identical up to rare +-1 levels
-    assert abs(float(outs[0][3]) - float(outs[1][3])) < 0.01
+    for k in (1, 2):
+        assert outs[0][0] == outs[k][0] and outs[0][1] == outs[k][1] and int(outs[0][1]) > 0   # hitpoints, deposits
+        assert abs(float(outs[0][3]) - float(outs[k][3])) < 0.01
+    a, b, c = (np.frombuffer((tmp_path / f"o{g}.ppm").read_bytes()[-160 * 120 * 3:], np.uint8) for g in ("1", "2p", "2n"))
+    assert np.abs(a.astype(int) - b.astype(int)).max() <= 1   # fp64 atomics + reduction order: identical up to rare +-1 levels
+    assert np.abs(a.astype(int) - c.astype(int)).max() <= 1
