@@ -539,10 +539,10 @@ def main():
     ap.add_argument("--cpu-photons", type=int, default=400000, help="photon budget of the CPU baseline sample (0 = skip)")
     ap.add_argument("--ref-photons", type=int, default=200000, help="photons per step of --impl reference")
     ap.add_argument("--shipped-photons", type=int, default=100000, help="total photons of the 'reference as shipped' leg (oracle/_ref; 0 = skip)")
-    ap.add_argument("--collective", default="peer", choices=["peer", "native", "torch"],
-                    help="N > 1: how the accumulators of a round are exchanged. peer: over peer memory inside the library, fused with the update and "
-                         "overlapped with the next round's trace (no collective call in a round); native: ncclAllReduce inside the library, in stream "
-                         "order; torch: torch.distributed all-reduce on the library's stream")
+    ap.add_argument("--collective", default="native", choices=["native", "peer", "torch"],
+                    help="N > 1: how the accumulators of a round are exchanged. native: ncclAllReduce inside the library, in stream order (fastest at "
+                         "8 GPUs); peer: over peer memory inside the library, fused with the update and overlapped with the next round's trace (no "
+                         "collective call in a round; fastest at 2 GPUs); torch: torch.distributed all-reduce on the library's stream")
     ap.add_argument("--f64-too", type=int, default=1, help="1: also time the same rounds with fp64 accumulators (value_f64_accumulators)")
     ap.add_argument("--e2e-rounds", type=int, default=-1, help="rounds of the end-to-end render() (default: the workload's own, c3 = 50; 0 = skip)")
     args = ap.parse_args()

@@ -1199,24 +1199,42 @@ __global__ void peer_wait_kernel(const int *my_flags, int world, int value, unsi
         if (t - t0 > timeout_ns) { atomicExch(err, 1 + g); return; }
     }
 }
-// acc.p[g] = rank g's accumulators of this round's parity; clear_next = this rank's accumulators of the other parity
+// acc.p[g] = rank g's accumulators of this round's parity; clear_next = this rank's accumulators of the other parity.
+// The remote loads of one hitpoint are issued together (eight float4 / four double4 in flight per thread) — one after the other they
+// cost a NVLink round trip each (measured at 8 GPUs: c2 5.17 ms per round against 4.71 with an in-stream ncclAllReduce). 64-thread
+// blocks so that a block fits into the registers the persistent emission kernel of the next round leaves free on an SM.
 template <int ACC>
-__global__ void __launch_bounds__(128) peer_reduce_update_kernel(unsigned int n, double alpha, HpArrays A, PeerPtrs acc, int world, void *__restrict__ clear_next) {
+__global__ void __launch_bounds__(64) peer_reduce_update_kernel(unsigned int n, double alpha, HpArrays A, const __grid_constant__ PeerPtrs acc, int world,
+                                                                void *__restrict__ clear_next) {
     unsigned int k = blockIdx.x * blockDim.x + threadIdx.x;
     if (k >= n) return;
     double dx = 0, dy = 0, dz = 0, m = 0;
     if (ACC == 0) {
-        for (int g = 0; g < world; g++) {
-            const double2 *ap = reinterpret_cast<const double2 *>(reinterpret_cast<const double4 *>(acc.p[g]) + k);
-            const double2 a0 = __ldcg(ap), a1 = __ldcg(ap + 1);
-            dx += a0.x; dy += a0.y; dz += a1.x; m += a1.y;
+        for (int g0 = 0; g0 < world; g0 += 4) {
+            double2 lo[4], hi[4];
+#pragma unroll
+            for (int j = 0; j < 4; j++) {
+                lo[j] = make_double2(0, 0); hi[j] = make_double2(0, 0);
+                if (g0 + j < world) {
+                    const double2 *ap = reinterpret_cast<const double2 *>(reinterpret_cast<const double4 *>(acc.p[g0 + j]) + k);
+                    lo[j] = __ldcg(ap); hi[j] = __ldcg(ap + 1);
+                }
+            }
+#pragma unroll
+            for (int j = 0; j < 4; j++) { dx += lo[j].x; dy += lo[j].y; dz += hi[j].x; m += hi[j].y; }  // rank order; an absent rank adds 0
         }
         reinterpret_cast<double4 *>(clear_next)[k] = make_double4(0, 0, 0, 0);
     } else {
         float fx = 0, fy = 0, fz = 0, fm = 0;  // float sums in rank order: what an all-reduce of float accumulators produces, identical on every rank
-        for (int g = 0; g < world; g++) {
-            const float4 a = __ldcg(reinterpret_cast<const float4 *>(acc.p[g]) + k);
-            fx += a.x; fy += a.y; fz += a.z; fm += a.w;
+        for (int g0 = 0; g0 < world; g0 += 8) {
+            float4 v[8];
+#pragma unroll
+            for (int j = 0; j < 8; j++) {
+                v[j] = make_float4(0, 0, 0, 0);
+                if (g0 + j < world) v[j] = __ldcg(reinterpret_cast<const float4 *>(acc.p[g0 + j]) + k);
+            }
+#pragma unroll
+            for (int j = 0; j < 8; j++) { fx += v[j].x; fy += v[j].y; fz += v[j].z; fm += v[j].w; }
         }
         dx = fx; dy = fy; dz = fz; m = fm;
         reinterpret_cast<float4 *>(clear_next)[k] = make_float4(0, 0, 0, 0);

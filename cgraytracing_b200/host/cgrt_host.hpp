@@ -311,8 +311,8 @@ struct RenderOptions {
                                          // (one GPU; `rounds` then only says how often filter radii are refreshed). false: one update per round
     uint64_t seed = 20261018ull;
     int device = 0;
-    bool peer_exchange = true;           // num_gpus > 1: exchange the accumulators of a round over peer memory, fused with the update
-                                         // (cgrt_peer_*); false: ncclAllReduce inside cgrt_round_update
+    bool peer_exchange = false;          // num_gpus > 1: false: ncclAllReduce inside cgrt_round_update (measured fastest at 8 GPUs); true: exchange
+                                         // the accumulators of a round over peer memory, fused with the update (cgrt_peer_*; fastest at 2 GPUs)
     int num_gpus = 1;                    // > 1: devices device .. device+num_gpus-1 of this box, one context and one host thread per GPU:
                                          // image rows and photon index ranges are split between them, NCCL (through the C ABI) carries the
                                          // hitpoint records and the per-round accumulators

@@ -24,7 +24,7 @@ int main(int argc, char **argv) {
     opt.width = std::atoi(argv[2]); opt.height = std::atoi(argv[3]);
     opt.num_photon = std::atoi(argv[4]); opt.num_threads = 1; opt.rounds = std::atoi(argv[5]);
     opt.num_gpus = argc > 8 ? std::atoi(argv[8]) : 1;  // > 1: rows and photon ranges split over that many GPUs of this box
-    opt.peer_exchange = !(argc > 9 && std::string(argv[9]) == "nccl");  // default: accumulators exchanged over peer memory
+    opt.peer_exchange = argc > 9 && std::string(argv[9]) == "peer";  // accumulators exchanged over peer memory instead of ncclAllReduce
     try {
         // floor texture: Texture(tdata, Vec3(0,1,0), Vec3(-21,0,0), 42, 40, false) — main.cpp:320 with ChessBoard.png
         int tw = 0, th = 0;

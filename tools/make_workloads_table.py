@@ -37,6 +37,17 @@ row(8, f"{P}_8gpu_strong.json", "c3, 16 Mi photons per round split over the GPUs
 for c, w, what in (("c1", "c1_spheres_bezier", "1 Mi photons per GPU per round"), ("c2", "c2_bunny_chess", "4 Mi photons per GPU per round")):
     row(8, f"{P}_8gpu_{c}.json", f"{c}, {what}, all-reduce on a side stream", "weak", one[w]["value"])
     row(8, f"{P}_8gpu_{c}_torch.json", f"{c}, {what}, all-reduce in stream order", "weak", one[w]["value"])
+row(2, f"{P}_2gpu_c2_nccl.json", "c2, ncclAllReduce in stream order (the library's default)", "weak", one["c2_bunny_chess"]["value"])
+row(2, f"{P}_2gpu_c2_peer.json", "c2, exchange over peer memory fused with the update", "weak", one["c2_bunny_chess"]["value"])
+row(2, f"{P}_2gpu_peer.json", "c3, exchange over peer memory fused with the update", "weak", c3["value"])
+row(8, f"{P}_8gpu_c2_nccl.json", "c2, ncclAllReduce in stream order (the library's default)", "weak", one["c2_bunny_chess"]["value"])
+row(8, f"{P}_8gpu_nccl2.json", "c3, ncclAllReduce in stream order (the library's default)", "weak", c3["value"])
+row(8, f"{P}_8gpu_c1_peer.json", "c1, peer exchange (remote loads one after the other)", "weak", one["c1_spheres_bezier"]["value"])
+row(8, f"{P}_8gpu_c2_peer.json", "c2, peer exchange (remote loads one after the other)", "weak", one["c2_bunny_chess"]["value"])
+row(8, f"{P}_8gpu_peer.json", "c3, peer exchange (remote loads one after the other)", "weak", c3["value"])
+row(8, f"{P}_8gpu_c1_peer2.json", "c1, peer exchange, remote loads issued together, side stream at the highest priority", "weak", one["c1_spheres_bezier"]["value"])
+row(8, f"{P}_8gpu_c2_peer2.json", "c2, peer exchange, remote loads issued together, side stream at the highest priority", "weak", one["c2_bunny_chess"]["value"])
+row(8, f"{P}_8gpu_peer2.json", "c3, peer exchange, remote loads issued together, side stream at the highest priority", "weak", c3["value"])
 row(8, f"{P}_8gpu_c4.json", "c4, 16 Mi photons per GPU per round", "weak", one["c4_bump_dof"]["value"])
 row(8, f"{P}_8gpu_c5.json", "c5, 1 Gi photons per round split over the GPUs", "strong", one["c5_dragon_4096"]["value"])
 r = L(f"{P}_8gpu_reference_arm.json")
@@ -44,6 +55,12 @@ out.append(f"\nThe rows marked `native` ran the all-reduce inside the library on
            f"in-stream collective (`torch` rows: same NCCL call, in stream order) on the short rounds of c1/c2 — NCCL's blocks cannot become resident next to the "
            f"persistent emission kernel — and the library now issues it in stream order. Reference arm under torchrun at N=8: {r['value']/1e6:.2f} M photons/s on "
            f"{r['cpu_baseline']['cores']} host threads with OMP_NUM_THREADS={r['cpu_baseline']['omp_num_threads_env']} in the environment (the thread count comes from the affinity mask).")
+out.append("\nThe exchange over peer memory (`cgrt_peer_*`: flags after the deposit kernel, one kernel on a side stream that reads every rank's accumulators over NVLink, "
+           "applies the update and clears the next buffer; `--collective peer`) is the faster one at 2 GPUs (c2: 4.12 vs 4.39 ms per round, 101 % of linear) and on "
+           "c1 at 8 GPUs (5.25 vs 5.54 ms), but loses to the in-stream ncclAllReduce on c2 and c3 at 8 GPUs (5.17 vs 4.71, 19.66 vs 19.12 ms): its reduce kernel "
+           "only becomes resident as the next round's trace kernels drain, and reads 8 x 17 MB per rank where the all-reduce moves 2 x 7/8 x 17 MB. Issuing the eight "
+           "remote loads of a hitpoint together helped c3 (19.24); giving the side stream the highest priority made c2 worse (8.06) and was taken out again. "
+           "`native` (ncclAllReduce inside `cgrt_round_update`, in stream order) is therefore the default of the library, of `bench.py` and of the C++ `render()`.")
 out.append("\nStrong scaling of c3 at 8 GPUs (2 Mi photons per GPU and round) is bound by the fixed part of a round: 11 trace launches whose late passes hold a few "
            "thousand rays, the 18 MB all-reduce and the update over all 1.13 M hitpoints (replicated) — 4.2 ms per round against 18.8 / 8 = 2.35 ms.")
 open("profiles/r02_workloads.md", "w").write("\n".join(out) + "\n")
