@@ -61,10 +61,10 @@ def load_peaks():
     return 6650.0, "fallback"
 
 
-def deposit_record_bytes():
+def deposit_record_bytes(ctx):
     from cgraytracing_b200.binding import load_library
 
-    return int(load_library().cgrt_deposit_record_bytes())
+    return int(load_library().cgrt_deposit_record_bytes(ctx.h))
 
 
 def load_ncu_traffic(photons, accum):
@@ -425,6 +425,7 @@ def run_gpu(args):
                        f"{world * P} photons + all-reduce + updates + fp64 image and 8-bit image download on every rank, wall clock, max over ranks"}
 
     photon_chunk = g.photon_chunk()
+    rec_b = deposit_record_bytes(g)
     g.close()  # every rank at the same point: with the peer exchange a context's shutdown is a handshake between the ranks
     if rank != 0:
         if world > 1:
@@ -442,7 +443,6 @@ def run_gpu(args):
     t_trace, t_dep, t_upd, t_sort = dt("photon_trace"), dt("photon_deposit"), dt("update"), dt("deposit_sort")
     t_emit, t_trav, t_cont = dt("trace_emit"), dt("trace_traverse"), dt("trace_continue")
     n_chunks = (P + photon_chunk - 1) // max(1, photon_chunk)
-    rec_b = deposit_record_bytes()
     # (1) SURVEY 8(d): bytes the REFERENCE's algorithm touches for the same work, in device-layout record sizes
     bytes_trace = seg * (B_SEGMENT + B_NODE * per_seg_nodes + B_TRI * per_seg_tris)
     bytes_dep_survey = gathered * B_CELLS + cand * B_CAND + dep * B_DEP

@@ -202,7 +202,8 @@ struct cgrt_ctx {
     // Deposit tables are double-buffered: the trace kernels of chunk k+1 (stream `tstream`) run while the sort + deposit kernels of
     // chunk k (stream `stream`) drain the other buffer — the latency-bound gather and the fp64-bound tracer share the SMs.
     struct DepBuf {
-        DepositRec *rec = nullptr;
+        char *rec = nullptr;          // deposit table: slots x deposit_rec_bytes(compact)
+        size_t rec_bytes = 0;         // bytes of one slot in this table
         uint32_t *keys = nullptr;     // bin per slot (CGRT_KEY_INVALID = empty)
         uint32_t *perm = nullptr;     // cell-grouped order of the valid slots
         uint32_t *hist = nullptr;     // CGRT_NBINS bin counters -> cursors
@@ -583,31 +584,34 @@ int ensure_queue(cgrt_ctx *ctx, int which, size_t cap) {
     ctx->q_cap[which] = cap;
     return 0;
 }
+// float accumulators with the per-round update: the 64-byte record (DepositRecC); everything else keeps the 96-byte fp64 record
+inline bool compact_records(const cgrt_ctx *ctx) { return ctx->cfg.accum_mode == 1 && ctx->cfg.update_mode != 0; }
 int ensure_photon_buffers(cgrt_ctx *ctx, size_t photons, size_t slots) {
+    const size_t rb = deposit_rec_bytes(compact_records(ctx));
     bool fresh = false;
     const int nbuf = ctx->overlap ? 2 : 1;  // the second deposit table only exists while the two-stream pipeline is on
     for (int bi = 0; bi < nbuf; bi++) {
         auto &b = ctx->dep[bi];
-        if (slots <= b.cap) continue;
+        if (slots <= b.cap && b.rec_bytes == rb) continue;
         CK(cudaStreamSynchronize(ctx->tstream));
         CK(cudaStreamSynchronize(ctx->stream));
         if (b.cap) {
-            big_give(ctx, b.cap * sizeof(DepositRec), b.rec);
+            big_give(ctx, b.cap * b.rec_bytes, b.rec);
             big_give(ctx, b.cap * sizeof(uint32_t), b.keys);
             big_give(ctx, b.cap * sizeof(uint32_t), b.perm);
         }
         b.cap = 0; b.rec = nullptr; b.keys = nullptr; b.perm = nullptr;  // nothing dangles if a block below cannot be had
-        DepositRec *nrec = (DepositRec *)big_take(ctx, slots * sizeof(DepositRec));
+        char *nrec = (char *)big_take(ctx, slots * rb);
         uint32_t *nkeys = (uint32_t *)big_take(ctx, slots * sizeof(uint32_t));
         uint32_t *nperm = (uint32_t *)big_take(ctx, slots * sizeof(uint32_t));
         if (!nrec || !nkeys || !nperm) {
-            big_give(ctx, slots * sizeof(DepositRec), nrec);
+            big_give(ctx, slots * rb, nrec);
             big_give(ctx, slots * sizeof(uint32_t), nkeys);
             big_give(ctx, slots * sizeof(uint32_t), nperm);
             FAIL(CGRT_ERR_CUDA, "out of device memory for the deposit tables");
         }
         b.rec = nrec; b.keys = nkeys; b.perm = nperm;
-        b.cap = slots;
+        b.cap = slots; b.rec_bytes = rb;
         b.drained_valid = false;
         fresh = true;
     }
@@ -819,7 +823,7 @@ int cgrt_destroy(cgrt_ctx *ctx) {
         if (b.traced) cudaEventDestroy(b.traced);
         if (b.drained) cudaEventDestroy(b.drained);
         if (b.cap) {
-            big_give(ctx, b.cap * sizeof(DepositRec), b.rec);
+            big_give(ctx, b.cap * b.rec_bytes, b.rec);
             big_give(ctx, b.cap * sizeof(uint32_t), b.keys);
             big_give(ctx, b.cap * sizeof(uint32_t), b.perm);
         }
@@ -1350,7 +1354,7 @@ static int photon_pass_impl(cgrt_ctx *ctx, uint64_t first, uint64_t count, const
     if (chunk == 0) {  // once per context: cudaMemGetInfo is not free
         size_t free_b = 0, total_b = 0;
         CK(cudaMemGetInfo(&free_b, &total_b));
-        const size_t per_photon = (size_t)P.max_depth * (sizeof(DepositRec) + 2 * sizeof(uint32_t)) * (ctx->overlap ? 2 : 1) + 2 * sizeof(PhotonState);
+        const size_t per_photon = (size_t)P.max_depth * (deposit_rec_bytes(compact_records(ctx)) + 2 * sizeof(uint32_t)) * (ctx->overlap ? 2 : 1) + 2 * sizeof(PhotonState);
         // what this context can actually get: free memory plus the blocks the arena holds for this device (a parked block is either
         // reused as it is or released on demand by arena_take), not the device's total — other contexts and frameworks share the GPU
         const size_t avail_b = free_b + arena_held(ctx->device);
@@ -1396,7 +1400,7 @@ static int photon_pass_impl(cgrt_ctx *ctx, uint64_t first, uint64_t count, const
         CK(cudaMemsetAsync(ctx->d_qcount + 2, 0, 12 * sizeof(unsigned int), T));
         unsigned int *qc = ctx->d_qcount + 2;
 #define LAUNCH_PT(F, GRID, QIN, NIN, QOUT, NOUT, CURSOR)                                                                            \
-    photon_trace_kernel<F><<<GRID, CGRT_PHOTON_BLOCK, 0, T>>>(ctx->S, P, base, (unsigned int)n, QIN, NIN, QOUT, NOUT, B.rec, B.keys, B.hist, \
+    photon_trace_kernel<F><<<GRID, CGRT_PHOTON_BLOCK, 0, T>>>(ctx->S, P, base, (unsigned int)n, QIN, NIN, QOUT, NOUT, B.rec, compact_records(ctx) ? 1 : 0, B.keys, B.hist, \
                                                              ctx->cull ? ctx->reach : nullptr, ctx->d_ctr, CURSOR)
         if (inj_org) {
             if (n != count) FAIL(CGRT_ERR_CAPACITY, "cgrt_trace: more rays than one launch holds");
@@ -1463,13 +1467,13 @@ static int photon_pass_impl(cgrt_ctx *ctx, uint64_t first, uint64_t count, const
             U1State U1;
             U1.cnt = ctx->A.cnt; U1.r2tab = ctx->r2tab; U1.cap = ctx->r2cap;
             if (ctx->cfg.update_mode == 0)
-                photon_deposit_kernel<2><<<dblocks, CGRT_DEPOSIT_BLOCK, 0, D>>>(P, B.rec, B.perm, B.nvalid, ctx->cell_start, ctx->A.pre, ctx->A.pre_n,
+                photon_deposit_kernel<2><<<dblocks, CGRT_DEPOSIT_BLOCK, 0, D>>>(P, reinterpret_cast<const DepositRec *>(B.rec), B.perm, B.nvalid, ctx->cell_start, ctx->A.pre, ctx->A.pre_n,
                                                                                 ctx->A.pre_f, ctx->A.hot, ctx->A.f, ctx->acc, ctx->d_ctr, U1);
             else if (ctx->cfg.accum_mode == 0)
-                photon_deposit_kernel<0><<<dblocks, CGRT_DEPOSIT_BLOCK, 0, D>>>(P, B.rec, B.perm, B.nvalid, ctx->cell_start, ctx->A.pre, ctx->A.pre_n,
+                photon_deposit_kernel<0><<<dblocks, CGRT_DEPOSIT_BLOCK, 0, D>>>(P, reinterpret_cast<const DepositRec *>(B.rec), B.perm, B.nvalid, ctx->cell_start, ctx->A.pre, ctx->A.pre_n,
                                                                                 ctx->A.pre_f, ctx->A.hot, ctx->A.f, ctx->acc, ctx->d_ctr, U1);
             else
-                photon_deposit_kernel<1><<<dblocks, CGRT_DEPOSIT_BLOCK, 0, D>>>(P, B.rec, B.perm, B.nvalid, ctx->cell_start, ctx->A.pre, ctx->A.pre_n,
+                photon_deposit_kernel<1><<<dblocks, CGRT_DEPOSIT_BLOCK, 0, D>>>(P, reinterpret_cast<const DepositRec *>(B.rec), B.perm, B.nvalid, ctx->cell_start, ctx->A.pre, ctx->A.pre_n,
                                                                                 ctx->A.pre_f, ctx->A.hot, ctx->A.f, ctx->acc, ctx->d_ctr, U1);
             ctx->launches++;
         } else if (ctx->profiling) {
@@ -1985,7 +1989,7 @@ int cgrt_release_cached_memory(int device, uint64_t *bytes_released) {
     return CGRT_OK;
 }
 
-int cgrt_deposit_record_bytes(void) { return (int)sizeof(DepositRec); }
+int cgrt_deposit_record_bytes(const cgrt_ctx *ctx) { return (int)deposit_rec_bytes(ctx != nullptr && compact_records(ctx)); }
 
 int cgrt_photon_chunk(cgrt_ctx *ctx, uint64_t *photons_per_launch) {
     if (!ctx || !photons_per_launch) return CGRT_ERR_INVALID;

@@ -322,6 +322,15 @@ struct __align__(32) DepositRec {
     int ix, iy, iz, pad0;            // hash.h:38-42 cell of pos
     double pad1;
 };
+// The record of the float-accumulator mode, 64 bytes = two sectors: the deposit is computed from the float flux there, so the flux travels as
+// three floats, and the cell is recomputed from the position by the consumer (four 16-byte loads per record instead of six, a third less of
+// the table to write and to read). Position and normal stay fp64: the rare pairs the float filters cannot decide take the reference's test.
+struct __align__(32) DepositRecC {
+    double pos[3], nrm[3];
+    float flux[3];
+    uint32_t pad;
+};
+__host__ __device__ __forceinline__ size_t deposit_rec_bytes(bool compact) { return compact ? sizeof(DepositRecC) : sizeof(DepositRec); }
 struct __align__(16) PhotonState {   // a suspended photon, 128 bytes
     double o[3], d[3], flux[3];      // the ray it was about to trace and the flux it carries
     double nearest, nrm[3];          // closest analytic hit so far (photon_traverse_kernel merges the meshes into it)
@@ -459,7 +468,7 @@ template <bool FIRST>
 __global__ void __launch_bounds__(CGRT_PHOTON_BLOCK, CGRT_TRACE_MINB) photon_trace_kernel(const __grid_constant__ SceneDev S, const __grid_constant__ PassParams P,
                                                                         uint64_t first_index, unsigned int n, const PhotonState *__restrict__ qin,
                                                                         const unsigned int *__restrict__ n_in, PhotonState *__restrict__ qout,
-                                                                        unsigned int *n_out, DepositRec *__restrict__ rec, uint32_t *__restrict__ keys,
+                                                                        unsigned int *n_out, char *__restrict__ rec, int compact, uint32_t *__restrict__ keys,
                                                                         uint32_t *__restrict__ hist, const uint32_t *__restrict__ reach, Counters *ctr,
                                                                         unsigned int *cursor) {
     const unsigned int total = FIRST ? n : *n_in;
@@ -595,11 +604,20 @@ __global__ void __launch_bounds__(CGRT_PHOTON_BLOCK, CGRT_TRACE_MINB) photon_tra
                 nhit++;
                 const bool reachable = (rword >> (rh & 31u)) & 1u;
                 if (reachable) {
-                    double2 *r = reinterpret_cast<double2 *>(rec + slot);  // streamed: written once, read once by the deposit kernel
-                    __stcs(r, make_double2(X.x, X.y)); __stcs(r + 1, make_double2(X.z, n_ff.x));
-                    __stcs(r + 2, make_double2(n_ff.y, n_ff.z)); __stcs(r + 3, make_double2(flux.x, flux.y));
-                    __stcs(r + 4, make_double2(flux.z, __longlong_as_double(((long long)(uint32_t)iy << 32) | (uint32_t)ix)));
-                    __stcs(r + 5, make_double2(__longlong_as_double((long long)(uint32_t)iz), 0.0));
+                    // streamed: written once, read once by the deposit kernel
+                    if (compact) {
+                        double2 *r = reinterpret_cast<double2 *>(rec + slot * sizeof(DepositRecC));
+                        __stcs(r, make_double2(X.x, X.y)); __stcs(r + 1, make_double2(X.z, n_ff.x)); __stcs(r + 2, make_double2(n_ff.y, n_ff.z));
+                        const long long f01 = ((long long)__float_as_uint((float)flux.y) << 32) | (long long)__float_as_uint((float)flux.x);
+                        const long long f2 = (long long)__float_as_uint((float)flux.z);
+                        __stcs(r + 3, make_double2(__longlong_as_double(f01), __longlong_as_double(f2)));
+                    } else {
+                        double2 *r = reinterpret_cast<double2 *>(rec + slot * sizeof(DepositRec));
+                        __stcs(r, make_double2(X.x, X.y)); __stcs(r + 1, make_double2(X.z, n_ff.x));
+                        __stcs(r + 2, make_double2(n_ff.y, n_ff.z)); __stcs(r + 3, make_double2(flux.x, flux.y));
+                        __stcs(r + 4, make_double2(flux.z, __longlong_as_double(((long long)(uint32_t)iy << 32) | (uint32_t)ix)));
+                        __stcs(r + 5, make_double2(__longlong_as_double((long long)(uint32_t)iz), 0.0));
+                    }
                     const uint32_t bin = cell_bin(ix, iy, iz);
                     keys[slot] = bin;
                     atomicAdd(hist + bin, 1u);  // histogram of the counting sort, fused into the producer
@@ -704,10 +722,13 @@ __device__ __forceinline__ ExactHit exact_hit(const HitShared<0> &H, uint32_t hl
 }
 __device__ __forceinline__ ExactHit exact_hit(const HitShared<2> &H, uint32_t hl, const DepositRec *r) { return exact_hit(static_cast<const HitShared<0> &>(H), hl, r); }
 __device__ __forceinline__ ExactHit exact_hit(const HitShared<1> &H, uint32_t hl, const DepositRec *__restrict__ rec) {
-    const double4 *r = reinterpret_cast<const double4 *>(rec + H.src[hl]);
-    double4 r0 = ldg4(r), r1 = ldg4(r + 1), r2 = ldg4(r + 2);
+    // float-accumulator mode: the table holds compact records (DepositRecC); the flux was rounded to float by the producer
+    const double2 *r = reinterpret_cast<const double2 *>(reinterpret_cast<const DepositRecC *>(rec) + H.src[hl]);
+    const double2 r0 = __ldcs(r), r1 = __ldcs(r + 1), r2 = __ldcs(r + 2), r3 = __ldcs(r + 3);
     ExactHit e;
-    e.X = mk(r0.x, r0.y, r0.z); e.nrm = mk(r0.w, r1.x, r1.y); e.flux = mk(r1.z, r1.w, r2.x);
+    e.X = mk(r0.x, r0.y, r1.x); e.nrm = mk(r1.y, r2.x, r2.y);
+    const long long f01 = __double_as_longlong(r3.x), f2 = __double_as_longlong(r3.y);
+    e.flux = mk((double)__uint_as_float((uint32_t)f01), (double)__uint_as_float((uint32_t)(f01 >> 32)), (double)__uint_as_float((uint32_t)f2));
     return e;
 }
 
@@ -885,22 +906,31 @@ __global__ void __launch_bounds__(CGRT_DEPOSIT_BLOCK, CGRT_DEPOSIT_MINB) photon_
             int ix = 0, iy = 0, iz = 0;
             if (valid) {
                 const uint32_t src = __ldcs(perm + j);
-                const double4 *r = reinterpret_cast<const double4 *>(rec + src);
-                double4 r0 = ldg4(r), r1 = ldg4(r + 1), r2 = ldg4(r + 2);  // streamed once
-                hx = (float)r0.x; hy = (float)r0.y; hz = (float)r0.z;
-                long long cxy = __double_as_longlong(r2.y);
-                ix = (int)(uint32_t)cxy; iy = (int)(uint32_t)(cxy >> 32); iz = (int)(uint32_t)__double_as_longlong(r2.z);
-                H.f[0][lane] = hx; H.f[1][lane] = hy; H.f[2][lane] = hz;
-                H.f[3][lane] = (float)r0.w; H.f[4][lane] = (float)r1.x; H.f[5][lane] = (float)r1.y;
-                if (ACC != 1) {
+                if (ACC == 1) {
+                    // compact record: position and normal fp64, flux as three floats; the cell is recomputed from the position (hash.h:38-42)
+                    const double2 *r = reinterpret_cast<const double2 *>(reinterpret_cast<const DepositRecC *>(rec) + src);
+                    const double2 r0 = __ldcs(r), r1 = __ldcs(r + 1), r2 = __ldcs(r + 2), r3 = __ldcs(r + 3);  // streamed once
+                    hx = (float)r0.x; hy = (float)r0.y; hz = (float)r1.x;
+                    cell_coord(mk(r0.x, r0.y, r1.x), P.celllength, P.inv_celllength, ix, iy, iz);
+                    H.f[0][lane] = hx; H.f[1][lane] = hy; H.f[2][lane] = hz;
+                    H.f[3][lane] = (float)r1.y; H.f[4][lane] = (float)r2.x; H.f[5][lane] = (float)r2.y;
+                    HitShared<1> &H1 = reinterpret_cast<HitShared<1> &>(H);
+                    const long long f01 = __double_as_longlong(r3.x), f2 = __double_as_longlong(r3.y);
+                    H1.f[6][lane] = __uint_as_float((uint32_t)f01); H1.f[7][lane] = __uint_as_float((uint32_t)(f01 >> 32));
+                    H1.f[8][lane] = __uint_as_float((uint32_t)f2);
+                    H1.src[lane] = src;
+                } else {
+                    const double4 *r = reinterpret_cast<const double4 *>(rec + src);
+                    double4 r0 = ldg4(r), r1 = ldg4(r + 1), r2 = ldg4(r + 2);  // streamed once
+                    hx = (float)r0.x; hy = (float)r0.y; hz = (float)r0.z;
+                    long long cxy = __double_as_longlong(r2.y);
+                    ix = (int)(uint32_t)cxy; iy = (int)(uint32_t)(cxy >> 32); iz = (int)(uint32_t)__double_as_longlong(r2.z);
+                    H.f[0][lane] = hx; H.f[1][lane] = hy; H.f[2][lane] = hz;
+                    H.f[3][lane] = (float)r0.w; H.f[4][lane] = (float)r1.x; H.f[5][lane] = (float)r1.y;
                     HitShared<0> &H0 = reinterpret_cast<HitShared<0> &>(H);
                     H0.v[0][lane] = r0.x; H0.v[1][lane] = r0.y; H0.v[2][lane] = r0.z;
                     H0.v[3][lane] = r0.w; H0.v[4][lane] = r1.x; H0.v[5][lane] = r1.y;
                     H0.v[6][lane] = r1.z; H0.v[7][lane] = r1.w; H0.v[8][lane] = r2.x;
-                } else {
-                    HitShared<1> &H1 = reinterpret_cast<HitShared<1> &>(H);
-                    H1.f[6][lane] = (float)r1.z; H1.f[7][lane] = (float)r1.w; H1.f[8][lane] = (float)r2.x;
-                    H1.src[lane] = src;
                 }
             }
             __syncwarp();

@@ -214,9 +214,9 @@ int cgrt_get_timings(cgrt_ctx *ctx, double ms[12]);
 int cgrt_check_guards(cgrt_ctx *ctx, uint64_t *damaged);
 /* Photons one trace launch of cgrt_photon_pass takes (sized from free device memory at the first pass; 0 before it). */
 int cgrt_photon_chunk(cgrt_ctx *ctx, uint64_t *photons_per_launch);
-/* Bytes of one slot of the deposit table (record written per recorded photon hit, read once by the gather): the unit of the
- * measurement's compulsory-traffic accounting. */
-int cgrt_deposit_record_bytes(void);
+/* Bytes of one slot of the deposit table (record written per recorded photon hit, read once by the gather) under the context's
+ * configuration — 64 with float accumulators, 96 with fp64 ones (NULL: 96): the unit of the measurement's compulsory-traffic accounting. */
+int cgrt_deposit_record_bytes(const cgrt_ctx *ctx);
 /* The library keeps the large device buffers of destroyed contexts (deposit tables, photon queues, ray queues) parked per device and
  * hands them to the next context: a render() creates and destroys one. Parked blocks are released automatically when an allocation
  * would otherwise fail; this call releases them now (device < 0: all devices). bytes_released may be NULL. */
