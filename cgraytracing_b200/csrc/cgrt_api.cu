@@ -206,7 +206,7 @@ struct cgrt_ctx {
         size_t rec_bytes = 0;         // bytes of one slot in this table
         uint32_t *keys = nullptr;     // bin per slot (CGRT_KEY_INVALID = empty)
         uint32_t *perm = nullptr;     // cell-grouped order of the valid slots
-        uint32_t *hist = nullptr;     // CGRT_NBINS bin counters -> cursors
+        uint32_t *hist = nullptr;     // bin counters -> cursors (P.bin_mask + 1 of them in use)
         uint32_t *bsum = nullptr;     // per-4096-bin block totals
         uint32_t *nvalid = nullptr;
         cudaEvent_t traced = nullptr, drained = nullptr;
@@ -634,8 +634,8 @@ int ensure_photon_buffers(cgrt_ctx *ctx, size_t photons, size_t slots) {
     }
     if (!ctx->dep[0].hist) {
         for (auto &b : ctx->dep) {
-            CKS(dalloc(ctx, &b.hist, (size_t)CGRT_NBINS));
-            CKS(dalloc(ctx, &b.bsum, (size_t)CGRT_NBINS / (CGRT_SCAN_BLOCK * CGRT_SCAN_ITEMS)));
+            CKS(dalloc(ctx, &b.hist, (size_t)1 << CGRT_BIN_BITS_MAX));
+            CKS(dalloc(ctx, &b.bsum, ((size_t)1 << CGRT_BIN_BITS_MAX) / (CGRT_SCAN_BLOCK * CGRT_SCAN_ITEMS)));
             CKS(dalloc(ctx, &b.nvalid, 2));
             CK(cudaEventCreateWithFlags(&b.traced, cudaEventDisableTiming));
             CK(cudaEventCreateWithFlags(&b.drained, cudaEventDisableTiming));
@@ -668,6 +668,7 @@ void derive_params(cgrt_ctx *ctx) {
     PassParams &P = ctx->P;
     P.width = c.width; P.height = c.height; P.max_depth = c.max_depth; P.samples = c.num_of_samples; P.use_dof = c.use_dof;
     P.hashsize = (uint32_t)c.hashsize;
+    P.bin_mask = (1u << (c.hashsize > (4 << 20) ? CGRT_BIN_BITS_MAX : CGRT_BIN_BITS_MIN)) - 1u;
     // Hashtable(hashsize, r): hash.h:22-30 with r = 200.0/height (main.cpp:183)
     double r = 200.0 / c.height;
     int cells = (int)(std::ceil(70.0 / r));
@@ -1396,7 +1397,7 @@ static int photon_pass_impl(cgrt_ctx *ctx, uint64_t first, uint64_t count, const
         auto mark = [&](cudaStream_t st) { if (timeline_on) { cudaEvent_t ev; cudaEventCreate(&ev); cudaEventRecord(ev, st); ctx->timeline.push_back(ev); } };
         mark(T);
         CK(cudaMemsetAsync(B.keys, 0xff, slots * sizeof(uint32_t), T));
-        CK(cudaMemsetAsync(B.hist, 0, (size_t)CGRT_NBINS * sizeof(uint32_t), T));
+        CK(cudaMemsetAsync(B.hist, 0, ((size_t)P.bin_mask + 1) * sizeof(uint32_t), T));
         CK(cudaMemsetAsync(ctx->d_qcount + 2, 0, 12 * sizeof(unsigned int), T));
         unsigned int *qc = ctx->d_qcount + 2;
 #define LAUNCH_PT(F, GRID, QIN, NIN, QOUT, NOUT, CURSOR)                                                                            \
@@ -1455,7 +1456,7 @@ static int photon_pass_impl(cgrt_ctx *ctx, uint64_t first, uint64_t count, const
         // the trace launches above read neither radii nor accumulators; the gather does: the previous round's update must have landed
         CKS(join_update(ctx));
         if (ctx->nhp > 0) {
-            const int nsb = (int)(CGRT_NBINS / (CGRT_SCAN_BLOCK * CGRT_SCAN_ITEMS));
+            const int nsb = (int)(((size_t)P.bin_mask + 1) / (CGRT_SCAN_BLOCK * CGRT_SCAN_ITEMS));
             bin_scan_blocks_kernel<<<nsb, CGRT_SCAN_BLOCK, 0, D>>>(B.hist, B.bsum);
             bin_scan_sums_kernel<<<1, CGRT_SCAN_BLOCK, 0, D>>>(B.bsum, nsb, B.nvalid);
             bin_scatter_kernel<<<ctx->deposit_grid, 256, 0, D>>>(B.keys, slots, B.hist, B.bsum, B.perm);

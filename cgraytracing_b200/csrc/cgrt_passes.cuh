@@ -43,6 +43,7 @@ __device__ __forceinline__ float prefilter_inner(double px, double py, double pz
 struct PassParams {
     int width, height, max_depth, samples, use_dof;
     uint32_t hashsize;
+    uint32_t bin_mask;     // counting-sort bins of the deposit table - 1 (2^22 or 2^23 bins)
     double celllength;     // Hashtable ctor result, hash.h:25-26
     double inv_celllength; // 1 / celllength (cell_floor_div)
     double r2_init;        // (200/height)^2, main.cpp:84,94
@@ -314,8 +315,11 @@ __global__ void reach_mark_kernel(const HpHot *__restrict__ hot, unsigned int n,
 // the same kernel; bin_scan_* + bin_scatter_kernel then turn it into the cell-grouped order the deposit kernel walks.
 // =================================================================================================================
 #define CGRT_KEY_INVALID 0xFFFFFFFFu  /* memset pattern of an empty slot */
-#define CGRT_BIN_BITS 22               /* counting-sort bins: 4 Mi counters = 16 MB, L2-resident */
-#define CGRT_NBINS (1u << CGRT_BIN_BITS)
+// Counting-sort bins: 2^22 (16 MB of counters, L2-resident) — 2^23 when the hash table is large (c5, 4096^2: 16x the cells of c3): more bins keep
+// the cells apart, so the deposit kernel's groups are larger (c5: 80 -> 67 ms per launch), but the producers' histogram atomics leave the
+// L2 (2^24: emission 37 -> 61 ms). PassParams::bin_mask carries the choice.
+#define CGRT_BIN_BITS_MIN 22
+#define CGRT_BIN_BITS_MAX 23
 
 struct __align__(32) DepositRec {
     double pos[3], nrm[3], flux[3];  // main.cpp:103-122: intersection, face-forwarded normal, photon flux
@@ -342,10 +346,10 @@ struct __align__(16) PhotonState {   // a suspended photon, 128 bytes
 // Bin of a deposit: any well-mixed CGRT_BIN_BITS-bit function of the cell. It only brings the records of one cell next to
 // each other (so one warp can reuse the cell's 27 candidate lists); correctness never depends on it, two cells sharing a
 // bin are told apart by their coordinates in the deposit kernel.
-__device__ __forceinline__ uint32_t cell_bin(int ix, int iy, int iz) {
+__device__ __forceinline__ uint32_t cell_bin(int ix, int iy, int iz, uint32_t bin_mask) {
     uint32_t h = (uint32_t)ix * 0x9E3779B1u ^ (uint32_t)iy * 0x85EBCA77u ^ (uint32_t)iz * 0xC2B2AE3Du;
     h ^= h >> 15; h *= 0x2C1B3C6Du; h ^= h >> 12;
-    return h & (CGRT_NBINS - 1u);
+    return h & bin_mask;
 }
 
 // The BVH part of the closest hit for suspended photons: one thread per queue entry, every lane traverses (dense warps,
@@ -618,7 +622,7 @@ __global__ void __launch_bounds__(CGRT_PHOTON_BLOCK, CGRT_TRACE_MINB) photon_tra
                         __stcs(r + 4, make_double2(flux.z, __longlong_as_double(((long long)(uint32_t)iy << 32) | (uint32_t)ix)));
                         __stcs(r + 5, make_double2(__longlong_as_double((long long)(uint32_t)iz), 0.0));
                     }
-                    const uint32_t bin = cell_bin(ix, iy, iz);
+                    const uint32_t bin = cell_bin(ix, iy, iz, P.bin_mask);
                     keys[slot] = bin;
                     atomicAdd(hist + bin, 1u);  // histogram of the counting sort, fused into the producer
                 }
@@ -1134,10 +1138,14 @@ __global__ void __launch_bounds__(CGRT_SCAN_BLOCK) bin_scan_blocks_kernel(uint32
 // phase 2: one block scans the (<= 1024) block totals; the grand total is the number of valid deposit slots
 __global__ void __launch_bounds__(CGRT_SCAN_BLOCK) bin_scan_sums_kernel(uint32_t *__restrict__ block_sums, int nblocks, uint32_t *__restrict__ n_valid) {
     __shared__ uint32_t ws[32];
-    uint32_t v = (int)threadIdx.x < nblocks ? block_sums[threadIdx.x] : 0u;
+    // every thread owns `per` consecutive block totals (1 for up to 2^22 bins)
+    const int per = (nblocks + CGRT_SCAN_BLOCK - 1) / CGRT_SCAN_BLOCK, first = (int)threadIdx.x * per;
+    uint32_t v = 0;
+    for (int j = 0; j < per; j++) v += first + j < nblocks ? block_sums[first + j] : 0u;
     uint32_t total;
     uint32_t ex = block_exclusive_scan_1024(v, ws, total);
-    if ((int)threadIdx.x < nblocks) block_sums[threadIdx.x] = ex;
+    for (int j = 0; j < per; j++)
+        if (first + j < nblocks) { const uint32_t c = block_sums[first + j]; block_sums[first + j] = ex; ex += c; }
     if (threadIdx.x == 0) { n_valid[0] = total; n_valid[1] = 0u; }  // [1]: the span cursor of photon_deposit_kernel
 }
 // phase 3 fused into the scatter: cursor of bin b = hist[b] + block_sums[b / 4096]
