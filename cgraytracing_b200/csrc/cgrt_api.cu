@@ -1178,12 +1178,14 @@ static int eye_wavefront(cgrt_ctx *ctx, size_t n, int depth0, int r0, bool gener
         CKS(ensure_queue(ctx, cur ^ 1, 2 * n > max_rays ? 2 * n : max_rays));  // glass splits: at most two children per ray
         CKS(ensure_hp_capacity(ctx, (size_t)ctx->hp_count + n));
         CK(cudaMemsetAsync(ctx->d_qcount + (cur ^ 1), 0, sizeof(unsigned int), ctx->stream));
-        if (generate && depth == depth0)
-            eye_bounce_kernel<true><<<nblk(n, 128), 128, 0, ctx->stream>>>(ctx->S, P, depth, ctx->q[cur], (unsigned int)n, r0, ctx->q[cur ^ 1],
-                                                                           ctx->d_qcount + (cur ^ 1), ctx->hp_rec, ctx->d_hp_count, ctx->hp_cap, ctx->d_ctr);
-        else
-            eye_bounce_kernel<false><<<nblk(n, 128), 128, 0, ctx->stream>>>(ctx->S, P, depth, ctx->q[cur], (unsigned int)n, r0, ctx->q[cur ^ 1],
-                                                                            ctx->d_qcount + (cur ^ 1), ctx->hp_rec, ctx->d_hp_count, ctx->hp_cap, ctx->d_ctr);
+        bool f32 = true;  // every tree within the float bound: the instantiation without fp64 box arithmetic
+        for (int b = 0; b < ctx->S.nbvh; b++) f32 = f32 && ctx->S.bvh[b].f32_ok;
+#define LAUNCH_EYE(FIRSTV, F32V)                                                                                                             \
+    eye_bounce_kernel<FIRSTV, F32V><<<nblk(n, 128), 128, 0, ctx->stream>>>(ctx->S, P, depth, ctx->q[cur], (unsigned int)n, r0, ctx->q[cur ^ 1], \
+                                                                          ctx->d_qcount + (cur ^ 1), ctx->hp_rec, ctx->d_hp_count, ctx->hp_cap, ctx->d_ctr)
+        if (generate && depth == depth0) { if (f32) LAUNCH_EYE(true, true); else LAUNCH_EYE(true, false); }
+        else { if (f32) LAUNCH_EYE(false, true); else LAUNCH_EYE(false, false); }
+#undef LAUNCH_EYE
         ctx->launches++;
         CK(cudaGetLastError());
         unsigned int counts[2];

@@ -760,7 +760,7 @@ __device__ __forceinline__ bool deferred_resolve(const SceneDev &S, int i, d3 o,
 }
 
 // Block-cooperative form (eye pass, parity hooks): every thread of the block must call it.
-template <int BLOCK, bool COUNT>
+template <int BLOCK, bool COUNT, bool F32 = false>
 __device__ __forceinline__ bool closest_hit_block(const SceneDev &S, bool active, d3 o, d3 d, Hit &h, TraceShared<BLOCK> &sm, TravCounters *tc) {
     HitAcc A;
     A.nearest = CGRT_INF; A.id = -1; A.prim = -1; A.nrm = mk(0, 0, 0);
@@ -807,7 +807,7 @@ __device__ __forceinline__ bool closest_hit_block(const SceneDev &S, bool active
             int s = sm.list[tid];
             HitAcc R;
             R.nearest = sm.near_in[s]; R.id = sm.id_in[s]; R.prim = -1; R.nrm = mk(0, 0, 0);
-            bool hit = deferred_resolve<COUNT, false>(S, i, mk(sm.ox[s], sm.oy[s], sm.oz[s]), mk(sm.dx[s], sm.dy[s], sm.dz[s]), sm.lim[s], R, tc);
+            bool hit = deferred_resolve<COUNT, false, F32>(S, i, mk(sm.ox[s], sm.oy[s], sm.oz[s]), mk(sm.dx[s], sm.dy[s], sm.dz[s]), sm.lim[s], R, tc);
             sm.leaf[s] = hit ? 1 : 0;
             if (hit) {
                 sm.lim[s] = R.nearest; sm.ox[s] = R.nrm.x; sm.oy[s] = R.nrm.y; sm.oz[s] = R.nrm.z; sm.id_in[s] = R.prim;

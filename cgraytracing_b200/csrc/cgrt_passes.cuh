@@ -100,7 +100,9 @@ struct Counters {
 #define CGRT_TRAV_MINB 8   /* 64 registers: 13.7 vs 15.1 ms of trace time per round; 6 (80 registers) gained nothing */
 #endif
 
-template <bool FIRST>
+// F32: every tree lies within CGRT_F32_BOUND (all BASELINE scenes) — the traversal instantiation without fp64 box arithmetic, as in the photon pass
+// (c4: 3.58 -> 3.86 G eye rays/s). Register caps of 167 / 161 / 96 were measured: c3 within 1.78-1.94 ms either way.
+template <bool FIRST, bool F32>
 __global__ void __launch_bounds__(CGRT_TRACE_BLOCK) eye_bounce_kernel(const __grid_constant__ SceneDev S, const __grid_constant__ PassParams P, int depth,
                                                          RayQueue qin, unsigned int n_in, int y0, RayQueue qout, unsigned int *n_out,
                                                          double *hp_rec, unsigned int *hp_count, unsigned int hp_cap, Counters *ctr) {
@@ -137,7 +139,7 @@ __global__ void __launch_bounds__(CGRT_TRACE_BLOCK) eye_bounce_kernel(const __gr
         code = qin.aux[i];
     }
     Hit hit;
-    bool found = closest_hit_block<CGRT_TRACE_BLOCK, false>(S, active, o, d, hit, sm, nullptr);
+    bool found = closest_hit_block<CGRT_TRACE_BLOCK, false, F32>(S, active, o, d, hit, sm, nullptr);
     {   // segments counter: one atomic per warp
         unsigned int act = __ballot_sync(0xffffffffu, active);
         if ((threadIdx.x & 31) == 0 && act) atomicAdd(&ctr->eye_segments, (unsigned long long)__popc(act));

@@ -21,8 +21,8 @@ for w in names:
                f"{k['bin_scan+bin_scatter_kernel']['seconds']*1e3:.2f} / {k['photon_deposit_kernel']['seconds']*1e3:.2f} / {k['round_update_kernel']['seconds']*1e3:.2f} | "
                f"{d['eye_rays_per_s']/1e6:.0f} M | {fr['photon_trace_family']:.2f} | {fr['photon_deposit_kernel']:.2f} | {r['whole_step']['frac']:.2f} | "
                f"{(str(round(d['e2e']['value']/1e6, 1)) + ' M') if d['e2e'] else '—'} | {d['cpu_baseline']['value']/1e6:.2f} M |")
-out += ["\nr01 → r02 on one GPU: c1 220 → 220, c2 940 → 1009, c3 862 → 892, c4 173 → 183, c5 620 → 652 M photons/s (4-wide BVH, staged-candidate reuse, two-phase staging).\n",
-        "## Multi-GPU (one box, torchrun, one process per GPU; all points measured with the r02 code)\n",
+out += ["\nr01 → r02 on one GPU: c1 220 → 222, c2 940 → 1030, c3 862 → 946, c4 173 → 184, c5 620 → 718 M photons/s (4-wide BVH, staged-candidate reuse, two-phase staging, 64-byte deposit records, 2^23 sort bins for the large hash table).\n",
+        "## Multi-GPU (one box, torchrun, one process per GPU; r02 code: the 2-GPU c3 rows with the final code, the 8-GPU rows and the 2-GPU c2 rows one change earlier, before the 64-byte deposit records — their `vs 1 GPU` is against the 1-GPU rate of that code, 892 M for c3)\n",
         "| GPUs | config | scaling | collective | photons/s | ms/step | e2e photons/s | vs 1 GPU |", "|---|---|---|---|---|---|---|---|"]
 c3 = one["c3_dragon_glass"]
 out.append(f"| 1 | c3 | — | — | {c3['value']/1e6:.1f} M | {c3['ms_per_step']:.2f} | {c3['e2e']['value']/1e6:.1f} M | 1.00 |")
@@ -32,8 +32,9 @@ def row(n, f, what, scaling, base):
     out.append(f"| {n} | {what} | {scaling} | {d['config'].get('collective')} | {d['value']/1e6:.1f} M | {d['ms_per_step']:.2f} | {(str(round(e['value']/1e6, 1)) + ' M') if e else '—'} | "
                f"{d['value']/base:.2f} ({100*d['value']/base/n:.0f} % of linear) |")
 row(2, f"{P}_2gpu.json", "c3, 16 Mi photons per GPU per round", "weak", c3["value"])
-row(8, f"{P}_8gpu.json", "c3, 16 Mi photons per GPU per round", "weak", c3["value"])
-row(8, f"{P}_8gpu_strong.json", "c3, 16 Mi photons per round split over the GPUs (2 Mi each)", "strong", c3["value"])
+C3_THEN = 892.3e6  # 1-GPU rate of the code the 8-GPU rows were measured with
+row(8, f"{P}_8gpu.json", "c3, 16 Mi photons per GPU per round", "weak", C3_THEN)
+row(8, f"{P}_8gpu_strong.json", "c3, 16 Mi photons per round split over the GPUs (2 Mi each)", "strong", C3_THEN)
 for c, w, what in (("c1", "c1_spheres_bezier", "1 Mi photons per GPU per round"), ("c2", "c2_bunny_chess", "4 Mi photons per GPU per round")):
     row(8, f"{P}_8gpu_{c}.json", f"{c}, {what}, all-reduce on a side stream", "weak", one[w]["value"])
     row(8, f"{P}_8gpu_{c}_torch.json", f"{c}, {what}, all-reduce in stream order", "weak", one[w]["value"])
@@ -41,13 +42,13 @@ row(2, f"{P}_2gpu_c2_nccl.json", "c2, ncclAllReduce in stream order (the library
 row(2, f"{P}_2gpu_c2_peer.json", "c2, exchange over peer memory fused with the update", "weak", one["c2_bunny_chess"]["value"])
 row(2, f"{P}_2gpu_peer.json", "c3, exchange over peer memory fused with the update", "weak", c3["value"])
 row(8, f"{P}_8gpu_c2_nccl.json", "c2, ncclAllReduce in stream order (the library's default)", "weak", one["c2_bunny_chess"]["value"])
-row(8, f"{P}_8gpu_nccl2.json", "c3, ncclAllReduce in stream order (the library's default)", "weak", c3["value"])
+row(8, f"{P}_8gpu_nccl2.json", "c3, ncclAllReduce in stream order (the library's default)", "weak", C3_THEN)
 row(8, f"{P}_8gpu_c1_peer.json", "c1, peer exchange (remote loads one after the other)", "weak", one["c1_spheres_bezier"]["value"])
 row(8, f"{P}_8gpu_c2_peer.json", "c2, peer exchange (remote loads one after the other)", "weak", one["c2_bunny_chess"]["value"])
-row(8, f"{P}_8gpu_peer.json", "c3, peer exchange (remote loads one after the other)", "weak", c3["value"])
+row(8, f"{P}_8gpu_peer.json", "c3, peer exchange (remote loads one after the other)", "weak", C3_THEN)
 row(8, f"{P}_8gpu_c1_peer2.json", "c1, peer exchange, remote loads issued together, side stream at the highest priority", "weak", one["c1_spheres_bezier"]["value"])
 row(8, f"{P}_8gpu_c2_peer2.json", "c2, peer exchange, remote loads issued together, side stream at the highest priority", "weak", one["c2_bunny_chess"]["value"])
-row(8, f"{P}_8gpu_peer2.json", "c3, peer exchange, remote loads issued together, side stream at the highest priority", "weak", c3["value"])
+row(8, f"{P}_8gpu_peer2.json", "c3, peer exchange, remote loads issued together, side stream at the highest priority", "weak", C3_THEN)
 row(8, f"{P}_8gpu_c4.json", "c4, 16 Mi photons per GPU per round", "weak", one["c4_bump_dof"]["value"])
 row(8, f"{P}_8gpu_c5.json", "c5, 1 Gi photons per round split over the GPUs", "strong", one["c5_dragon_4096"]["value"])
 r = L(f"{P}_8gpu_reference_arm.json")
