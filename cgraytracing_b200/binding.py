@@ -124,6 +124,8 @@ class Context:
             setattr(k, f, int(getattr(cfg, f)))
         k.accum_mode = int(getattr(cfg, "accum_mode", 0) if accum_mode is None else accum_mode)
         k.update_mode = int(getattr(cfg, "update_mode", 1))  # 0: the reference's per-photon update (U1), 1: per round (U2)
+        if k.update_mode == 0:
+            k.accum_mode = 0  # the library keeps fp64 sums in that mode whatever is asked for; keep this side's view of the buffer in step
         k.alpha, k.focus_plane, k.lens_radius = cfg.alpha, cfg.focus_plane, cfg.lens_radius
         k.lightorg = (C.c_double * 3)(*cfg.lightorg)
         k.camorg = (C.c_double * 3)(*cfg.camorg)
