@@ -43,7 +43,9 @@ out.append("""## 5. Reading
   (three unconditional stack stores per node: +11 %) and to occupancy (80 registers: +35 %), not to instruction count (fused slabs: flat).
 * photon_deposit_kernel is bound by the LSU data pipe (`l1tex__data_pipe_lsu_wavefronts` ~ 92 % of peak: half shared-memory loads — the
   broadcast prefilter scan costs four wavefronts per staged candidate —, the rest record gathers, staging loads and one `red` per deposit).
-  r02 removed per-group work (a cell's staged list is reused by the following batches; filter records only for culled survivors).
+  r02 removed per-group work (a cell's staged list is reused by the following batches; filter records only for culled survivors), a third of
+  the record bytes (64-byte records: four loads instead of six) and, with float accumulators, the pair queue and the shared-memory copy of the hits
+  (every lane walks its own surviving pairs from registers).
 """)
 
 open(f"profiles/{tag}_ncu_summary.md", "w").write("\n".join(out))
