@@ -312,8 +312,8 @@ __global__ void reach_mark_kernel(const HpHot *__restrict__ hot, unsigned int n,
 // Photon k always draws Philox stream (seed, PASS_PHOTON, k, bounce): any partition of [first, first+count) over
 // launches, queues, chunks or GPUs produces the same deposits.
 //
-// Deposits go to a dense, deterministic table: slot = depth * n + k (k = photon number inside the launch), 96-byte
-// record + 32-bit bin; empty slots keep CGRT_KEY_INVALID (pre-filled by a memset). The bin histogram is accumulated by
+// Deposits go to a dense, deterministic table: slot = depth * n + k (k = photon number inside the launch), 64- or 96-byte
+// record (DepositRecC / DepositRec) + 32-bit bin; empty slots keep CGRT_KEY_INVALID (pre-filled by a memset). The bin histogram is accumulated by
 // the same kernel; bin_scan_* + bin_scatter_kernel then turn it into the cell-grouped order the deposit kernel walks.
 // =================================================================================================================
 #define CGRT_KEY_INVALID 0xFFFFFFFFu  /* memset pattern of an empty slot */
@@ -480,7 +480,7 @@ __global__ void __launch_bounds__(CGRT_PHOTON_BLOCK, CGRT_TRACE_MINB) photon_tra
     const unsigned int total = FIRST ? n : *n_in;
     // Work is handed out from the head of the index range: a warp draws CGRT_FETCH consecutive indices at a time from a global cursor
     // (one atomic per CGRT_FETCH photons) and its lanes take them in order. With a static stride per thread the lanes of the grid drift
-    // apart (a photon lives 1 to 5 segments) and after ~1000 photons per thread their deposit records, 96-byte scattered stores, are
+    // apart (a photon lives 1 to 5 segments) and after ~1000 photons per thread their deposit records, 64- to 96-byte scattered stores, are
     // spread over gigabytes of the table: the emission kernel went from 5.6 to 8.0 ms per 16 Mi photons between 16 Mi and 64 Mi chunks.
     const unsigned int lane_id = threadIdx.x & 31u, lt_mask = (1u << lane_id) - 1u;
     unsigned int wnext = 0, wend = 0;
@@ -686,7 +686,7 @@ __global__ void __launch_bounds__(CGRT_PHOTON_BLOCK, CGRT_TRACE_MINB) photon_tra
 // ---------------------------------------------------------------------------------------------------------------------
 #define CGRT_DEPOSIT_BLOCK 256
 #ifndef CGRT_DEPOSIT_MINB
-#define CGRT_DEPOSIT_MINB 4   /* resident blocks per SM asked of ptxas (64 registers; 5 = 48 registers was measured: 6.54 vs 6.45 ms) */
+#define CGRT_DEPOSIT_MINB 4   /* resident blocks per SM asked of ptxas (64 registers). Measured with the final kernel: 3 (78 registers) 5.92 ms, 4: 5.45 ms, 5 (48 registers, spills) 5.75 ms, 6: 6.17 ms */
 #endif
 #ifndef CGRT_DEPOSIT_SPAN
 #define CGRT_DEPOSIT_SPAN 256   /* sorted records a warp takes from the cursor at a time. Measured 64 / 128 / 256 / 512 / 1024 / 2048 / 4096: 9.2 / 7.25 / 6.45 / 6.45 / 6.6 / 6.95 / 7.2 ms: consecutive batches of a warp hit the same candidate lists in L1, long spans balance worse */
