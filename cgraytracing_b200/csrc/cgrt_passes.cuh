@@ -1053,7 +1053,7 @@ __global__ void __launch_bounds__(CGRT_DEPOSIT_BLOCK, CGRT_DEPOSIT_MINB) photon_
                         }
                     }
                     if (!((grp >> lane) & 1u)) { m_lo = 0; m_hi = 0; }
-                    if (ACC == 1) {
+                    if constexpr (ACC == 1) {
                         // Float accumulators: every lane walks the candidates that passed its own prefilter, its hit in registers — no pair
                         // queue and no shared-memory copy of the hits. The lanes idle while the busiest one finishes (4.8 pairs per hit
                         // on average, ~10 at most), but the shared-memory traffic of the queue form costs more on the pipe that bounds
@@ -1095,8 +1095,7 @@ __global__ void __launch_bounds__(CGRT_DEPOSIT_BLOCK, CGRT_DEPOSIT_MINB) photon_
                         npair += (lane == 0) ? mine : 0u;
                         __syncwarp();
                         if (reuse || c0 >= total) break;
-                        continue;
-                    }
+                    } else {
                     // ---- drain: one surviving pair per lane and round into the queue; 32 queued pairs = one exact step
                     while (__any_sync(0xffffffffu, (m_lo | m_hi) != 0u)) {
                         const bool has = (m_lo | m_hi) != 0u;
@@ -1120,6 +1119,7 @@ __global__ void __launch_bounds__(CGRT_DEPOSIT_BLOCK, CGRT_DEPOSIT_MINB) photon_
                     qn = 0;
                     __syncwarp();
                     if (reuse || c0 >= total) break;
+                    }
                 }
             }
         }
