@@ -25,6 +25,22 @@ def test_reference_arm_prints_exactly_one_json_line():
     assert d["e2e"]["value"] == d["value"] and d["e2e"]["h2d_bytes_per_step"] == 0 and d["e2e"]["d2h_bytes_per_step"] == 0
 
 
+def test_reference_arm_uses_every_host_core_under_torchrun_and_times_the_reference_as_shipped():
+    """torch.distributed.run exports OMP_NUM_THREADS=1 to its workers: the CPU arm must still use the cores the process may run on (affinity
+    mask), and carry the unmodified reference's own photon loop (oracle/_ref, main.cpp:222-249) beside the port."""
+    env = dict(os.environ, OMP_NUM_THREADS="1")
+    r = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--impl", "reference", "--steps", "1", "--warmup", "1", "--ref-photons", "4000",
+                        "--shipped-photons", "2000", "--workload", "c2_bunny_chess"], capture_output=True, text=True, timeout=600, cwd=ROOT, env=env)
+    assert r.returncode == 0, r.stderr[-2000:]
+    d = json.loads([l for l in r.stdout.splitlines() if l.strip()][-1])
+    cb = d["cpu_baseline"]
+    assert cb["cores"] == len(os.sched_getaffinity(0)) and cb["omp_num_threads_env"] == "1"
+    assert cb["kind"] == "port" and cb["deposits_per_hit"] > 0
+    if os.path.exists(os.path.join(ROOT, "oracle", "_ref", "libcgref.so")):
+        sh = cb["as_shipped"]
+        assert sh["kind"] == "reference" and sh["value"] > 0 and sh["cores"] == cb["cores"] and sh["hitpoints"] > 0
+
+
 def test_b200_arm_fails_loudly_without_a_gpu():
     import torch
     if torch.cuda.is_available():
