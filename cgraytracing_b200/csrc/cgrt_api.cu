@@ -615,6 +615,7 @@ int ensure_photon_buffers(cgrt_ctx *ctx, size_t photons, size_t slots) {
         b.drained_valid = false;
         fresh = true;
     }
+    photons += CGRT_QHOLE_MARGIN;  // room for the slots warps reserve and do not use
     if (photons > ctx->pq_cap) {
         CK(cudaStreamSynchronize(ctx->tstream));
         for (int k = 0; k < 2; k++) {

@@ -337,6 +337,13 @@ struct __align__(32) DepositRecC {
     uint32_t pad;
 };
 __host__ __device__ __forceinline__ size_t deposit_rec_bytes(bool compact) { return compact ? sizeof(DepositRecC) : sizeof(DepositRec); }
+// Slots of the suspend queue are reserved per warp AHEAD of need (CGRT_QRES at a time, the next range requested while the current one still has
+// 32 free slots), so a suspension never waits for its atomic's round trip to the L2 (7 % of the trace kernels' samples before). What a warp
+// has reserved and not used when it exits is marked as holes (depth = CGRT_QHOLE), which the consumers skip; the photon queues carry
+// CGRT_QHOLE_MARGIN entries beyond the photon count for them.
+#define CGRT_QRES 64u
+#define CGRT_QHOLE 0xFFFFFFFFu
+#define CGRT_QHOLE_MARGIN ((size_t)1 << 19)
 struct __align__(16) PhotonState {   // a suspended photon, 128 bytes
     double o[3], d[3], flux[3];      // the ray it was about to trace and the flux it carries
     double nearest, nrm[3];          // closest analytic hit so far (photon_traverse_kernel merges the meshes into it)
@@ -370,6 +377,7 @@ __global__ void __launch_bounds__(128, CGRT_TRAV_MINB) photon_traverse_kernel(co
     for (unsigned int i = blockIdx.x * blockDim.x + threadIdx.x; i < total; i += gridDim.x * blockDim.x) {
         // Only (nearest, id) of the running closest hit stay in registers across a traversal; the ray is re-read from the queue entry
         // (L1) for every tree, and a closer hit is written back at once.
+        if (q[i].depth == CGRT_QHOLE) continue;  // a reserved slot nobody used
         double nearest = q[i].nearest;
         int id = q[i].id;
         for (int k = 0; k < S.nobj; k++) {
@@ -409,7 +417,7 @@ __global__ void __launch_bounds__(128) photon_bezier_kernel(const __grid_constan
     const unsigned int rounds = (total + nhalf - 1) / nhalf;
     for (unsigned int r = 0; r < rounds; r++) {  // both halves of a warp run the same number of rounds: shuffles stay convergent
         const unsigned int i = r * nhalf + half;
-        const bool live = i < total;
+        const bool live = i < total && q[i].depth != CGRT_QHOLE;
         d3 o = mk(0, 0, 0), d = mk(0, 0, 1);
         double nearest = CGRT_INF;
         int id = -1;
@@ -485,6 +493,9 @@ __global__ void __launch_bounds__(CGRT_PHOTON_BLOCK, CGRT_TRACE_MINB) photon_tra
     const unsigned int lane_id = threadIdx.x & 31u, lt_mask = (1u << lane_id) - 1u;
     unsigned int wnext = 0, wend = 0;
     bool exhausted = false;
+    unsigned int rs = 0, re = 0, nb_reg = 0;  // reserved slots [rs, re) of the output queue (warp-uniform); lane 0 holds the pending next range
+    bool res_pending = false;
+    const unsigned int qres = total < (1u << 20) ? 32u : CGRT_QRES;  // short queues: fewer holes
     // at most CGRT_FETCH, and small enough that every warp of the grid gets about four turns (the late passes of a round have short queues)
     unsigned int fetch = total / (((gridDim.x * CGRT_PHOTON_BLOCK) >> 5) * 4u);
     fetch = fetch > (unsigned int)CGRT_FETCH ? (unsigned int)CGRT_FETCH : (fetch < 32u ? 32u : (fetch & ~31u));
@@ -535,6 +546,7 @@ __global__ void __launch_bounds__(CGRT_PHOTON_BLOCK, CGRT_TRACE_MINB) photon_tra
                         uint64_t meta = (uint64_t)__double_as_longlong(__ldg(reinterpret_cast<const double *>(q + 7)));
                         local = (uint32_t)meta; depth = (int)(meta >> 32);
                         mode = PH_RESOLVED;  // arrives with the closest hit of its pending segment
+                        if ((uint32_t)(meta >> 32) == CGRT_QHOLE) { mode = PH_NEED; want = true; }  // a reserved slot nobody used: take another
                     }
                 }
                 wnext += cnt < avail ? cnt : avail;
@@ -573,14 +585,27 @@ __global__ void __launch_bounds__(CGRT_PHOTON_BLOCK, CGRT_TRACE_MINB) photon_tra
                 if (deferred_wanted(S, S.deferred_ix[k], o, d, A, lim)) { suspended = true; break; }
             }
         }
-        {   // suspend in front of a mesh: compact into the next queue (warp ballot + one atomic per warp)
+        {   // suspend in front of a mesh: compact into the next queue (warp ballot; slots from the warp's reservation)
             unsigned int m = __ballot_sync(0xffffffffu, suspended);
+            unsigned int slot = 0;
+            if (m) {  // warp-uniform
+                const unsigned int cnt = (unsigned int)__popc(m), avail = re - rs, rank = (unsigned int)__popc(m & lt_mask);
+                unsigned int nb = 0;
+                if (avail < cnt) {  // the next range is needed: normally requested long ago
+                    if (!res_pending && lane_id == 0) nb_reg = atomicAdd(n_out, qres);
+                    nb = __shfl_sync(0xffffffffu, nb_reg, 0);
+                    res_pending = false;
+                }
+                slot = rank < avail ? rs + rank : nb + (rank - avail);
+                if (avail < cnt) { rs = nb + (cnt - avail); re = nb + qres; }
+                else rs += cnt;
+                if (!res_pending && re - rs < 32u) {  // ask for the next range now, look at the answer when it is needed
+                    if (lane_id == 0) nb_reg = atomicAdd(n_out, qres);
+                    res_pending = true;
+                }
+            }
             if (suspended) {
-                int lane = threadIdx.x & 31, leader = __ffs(m) - 1;
-                unsigned int base = 0;
-                if (lane == leader) base = atomicAdd(n_out, (unsigned int)__popc(m));
-                base = __shfl_sync(m, base, leader);
-                double2 *q = reinterpret_cast<double2 *>(qout + base + __popc(m & ((1u << lane) - 1u)));
+                double2 *q = reinterpret_cast<double2 *>(qout + slot);
                 uint64_t meta = ((uint64_t)(uint32_t)depth << 32) | (uint64_t)local;
                 long long ip = ((long long)(uint32_t)A.prim << 32) | (long long)(uint32_t)A.id;
                 q[0] = make_double2(o.x, o.y); q[1] = make_double2(o.z, d.x); q[2] = make_double2(d.y, d.z);
@@ -658,6 +683,14 @@ __global__ void __launch_bounds__(CGRT_PHOTON_BLOCK, CGRT_TRACE_MINB) photon_tra
             depth++;
         } else if (!done) {
             mode = PH_NEED;  // suspended, or the ray left the scene (main.cpp:64-66)
+        }
+    }
+    {   // what this warp reserved and did not use: holes
+        const double2 hole = make_double2(__longlong_as_double((long long)((uint64_t)CGRT_QHOLE << 32)), 0.0);
+        for (unsigned int s = rs + lane_id; s < re; s += 32u) reinterpret_cast<double2 *>(qout + s)[7] = hole;
+        if (res_pending) {
+            const unsigned int nb = __shfl_sync(0xffffffffu, nb_reg, 0);
+            for (unsigned int s = nb + lane_id; s < nb + qres; s += 32u) reinterpret_cast<double2 *>(qout + s)[7] = hole;
         }
     }
     // ---- counters: warp reduce, one atomic per warp and counter
