@@ -21,7 +21,7 @@ for w in names:
                f"{k['bin_scan+bin_scatter_kernel']['seconds']*1e3:.2f} / {k['photon_deposit_kernel']['seconds']*1e3:.2f} / {k['round_update_kernel']['seconds']*1e3:.2f} | "
                f"{d['eye_rays_per_s']/1e6:.0f} M | {fr['photon_trace_family']:.2f} | {fr['photon_deposit_kernel']:.2f} | {r['whole_step']['frac']:.2f} | "
                f"{(str(round(d['e2e']['value']/1e6, 1)) + ' M') if d['e2e'] else '—'} | {d['cpu_baseline']['value']/1e6:.2f} M |")
-out += ["\nr01 → r02 on one GPU: c1 220 → 222, c2 940 → 1030, c3 862 → 946, c4 173 → 184, c5 620 → 718 M photons/s (4-wide BVH, staged-candidate reuse, two-phase staging, 64-byte deposit records, 2^23 sort bins for the large hash table).\n",
+out += ["\nr01 → r02 on one GPU: c1 220 → 222, c2 940 → 1030, c3 862 → 967, c4 173 → 184, c5 620 → 718 M photons/s (4-wide BVH, staged-candidate reuse, two-phase staging, 64-byte deposit records, 2^23 sort bins for the large hash table).\n",
         "## Multi-GPU (one box, torchrun, one process per GPU; r02 code: the 2-GPU c3 rows with the final code, the 8-GPU rows and the 2-GPU c2 rows one change earlier, before the 64-byte deposit records — their `vs 1 GPU` is against the 1-GPU rate of that code, 892 M for c3)\n",
         "| GPUs | config | scaling | collective | photons/s | ms/step | e2e photons/s | vs 1 GPU |", "|---|---|---|---|---|---|---|---|"]
 c3 = one["c3_dragon_glass"]
